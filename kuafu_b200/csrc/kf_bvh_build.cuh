@@ -1,0 +1,619 @@
+// kf_bvh_build.cuh -- device construction of the acceleration structures that replace
+// VkAccelerationStructureKHR BLAS/TLAS (reference src/core/rt/rt.cpp:142-370 build + compaction,
+// :372-495 per-frame TLAS update).
+//
+// Pipeline (all kernels here; the host only sequences launches):
+//   primitive boxes -> scene box (ordered-int atomics) -> 63-bit Morton keys -> LSD radix sort
+//   -> Karras LBVH hierarchy -> bottom-up boxes (atomic arrival counters)
+//   -> level-by-level collapse into 8-wide nodes (largest-area-first expansion, leaves <= 3 prims,
+//      octant slot assignment, 8-bit quantisation) -> triangles re-laid in leaf order.
+// Refit keeps the binary topology and the slot assignment, recomputes boxes bottom-up and
+// re-quantises every wide node.
+#pragma once
+
+#include "kf_common.cuh"
+
+namespace kf {
+
+// -------------------------------------------------------------------------------------------------
+// helpers
+// -------------------------------------------------------------------------------------------------
+struct Box6 {
+  float lo[3], hi[3];
+};
+KF_D void boxReset(Box6& b) {
+  b.lo[0] = b.lo[1] = b.lo[2] = 3.0e38f;
+  b.hi[0] = b.hi[1] = b.hi[2] = -3.0e38f;
+}
+KF_D void boxGrow(Box6& b, const Box6& o) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = fminf(b.lo[k], o.lo[k]);
+    b.hi[k] = fmaxf(b.hi[k], o.hi[k]);
+  }
+}
+KF_D float boxArea(const Box6& b) {
+  float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+// Conservative margin: culling must never reject a primitive the float triangle test accepts.
+KF_D void boxPad(Box6& b) {
+  float m = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) m = fmaxf(m, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k])));
+  float pad = m * (1.0f / 16384.0f) + 1e-30f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] -= pad;
+    b.hi[k] += pad;
+  }
+}
+KF_D Box6 loadBox(const float* p) {
+  Box6 b;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = p[k];
+    b.hi[k] = p[3 + k];
+  }
+  return b;
+}
+KF_D Box6 loadBoxCG(const float* p) {
+  Box6 b;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = __ldcg(p + k);
+    b.hi[k] = __ldcg(p + 3 + k);
+  }
+  return b;
+}
+KF_D void storeBox(float* p, const Box6& b) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    p[k] = b.lo[k];
+    p[3 + k] = b.hi[k];
+  }
+}
+// float <-> order-preserving int for atomicMin/atomicMax
+KF_D int floatToOrdered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+KF_D float orderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// -------------------------------------------------------------------------------------------------
+// primitive setup
+// -------------------------------------------------------------------------------------------------
+// One thread per triangle: padded box + contribution to the scene box.
+__global__ void k_tri_boxes(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
+                            uint32_t nTris, float* __restrict__ primBox, int* __restrict__ sceneBox) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nTris) return;
+  Box6 b;
+  boxReset(b);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float* p = verts[idx[3 * t + c]].pos;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      b.lo[k] = fminf(b.lo[k], p[k]);
+      b.hi[k] = fmaxf(b.hi[k], p[k]);
+    }
+  }
+  boxPad(b);
+  storeBox(primBox + 6 * t, b);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    atomicMin(sceneBox + k, floatToOrdered(b.lo[k]));
+    atomicMax(sceneBox + 3 + k, floatToOrdered(b.hi[k]));
+  }
+}
+
+__global__ void k_init_scene_box(int* sceneBox) {
+  if (threadIdx.x < 3) sceneBox[threadIdx.x] = floatToOrdered(3.0e38f);
+  else if (threadIdx.x < 6) sceneBox[threadIdx.x] = floatToOrdered(-3.0e38f);
+}
+
+// World->object matrix, world box (from the 8 corners of the BLAS root box) and InstRec of every
+// instance.  The inverse follows the float cofactor contract of oracle affineInverse().
+struct BlasInfo {
+  const Node8* nodes;
+  const Tri48* tris;
+  float box[6];
+  uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque
+  uint32_t pad;
+};
+__global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_t n,
+                                 const BlasInfo* __restrict__ blas, uint32_t nBlas,
+                                 InstRec* __restrict__ recs, float* __restrict__ primBox,
+                                 int* __restrict__ sceneBox) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* m = insts[i].transform;
+  const float a00 = m[0], a10 = m[1], a20 = m[2];
+  const float a01 = m[4], a11 = m[5], a21 = m[6];
+  const float a02 = m[8], a12 = m[9], a22 = m[10];
+  const float t0 = m[12], t1 = m[13], t2 = m[14];
+  const float c00 = csub(cmul(a11, a22), cmul(a12, a21));
+  const float c01 = csub(cmul(a12, a20), cmul(a10, a22));
+  const float c02 = csub(cmul(a10, a21), cmul(a11, a20));
+  const float det = cadd(cadd(cmul(a00, c00), cmul(a01, c01)), cmul(a02, c02));
+  const float id = cdiv(1.0f, det);
+  float inv[3][4];
+  inv[0][0] = cmul(c00, id);
+  inv[1][0] = cmul(c01, id);
+  inv[2][0] = cmul(c02, id);
+  inv[0][1] = cmul(csub(cmul(a02, a21), cmul(a01, a22)), id);
+  inv[1][1] = cmul(csub(cmul(a00, a22), cmul(a02, a20)), id);
+  inv[2][1] = cmul(csub(cmul(a01, a20), cmul(a00, a21)), id);
+  inv[0][2] = cmul(csub(cmul(a01, a12), cmul(a02, a11)), id);
+  inv[1][2] = cmul(csub(cmul(a02, a10), cmul(a00, a12)), id);
+  inv[2][2] = cmul(csub(cmul(a00, a11), cmul(a01, a10)), id);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    inv[r][3] = -cadd(cadd(cmul(inv[r][0], t0), cmul(inv[r][1], t1)), cmul(inv[r][2], t2));
+  InstRec rec;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) rec.inv[4 * r + c] = inv[r][c];
+  const uint32_t g = insts[i].geometryIndex;
+  Box6 wb;
+  bool usable = g < nBlas && (blas[g].flags & 1u);
+  if (usable) {
+    rec.nodes = blas[g].nodes;
+    rec.tris = reinterpret_cast<const Tri48*>(reinterpret_cast<uintptr_t>(blas[g].tris) |
+                                              ((blas[g].flags & 2u) ? 1ull : 0ull));
+    boxReset(wb);
+    const float* ob = blas[g].box;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const float x = (c & 1) ? ob[3] : ob[0];
+      const float y = (c & 2) ? ob[4] : ob[1];
+      const float z = (c & 4) ? ob[5] : ob[2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float p = ((m[k] * x + m[4 + k] * y) + m[8 + k] * z) + m[12 + k];
+        wb.lo[k] = fminf(wb.lo[k], p);
+        wb.hi[k] = fmaxf(wb.hi[k], p);
+      }
+    }
+    boxPad(wb);
+  } else {
+    rec.nodes = nullptr;
+    rec.tris = nullptr;
+    // a point box at the first usable... keep it harmless: degenerate box at the origin
+#pragma unroll
+    for (int k = 0; k < 3; k++) wb.lo[k] = wb.hi[k] = 0.0f;
+  }
+  recs[i] = rec;
+  storeBox(primBox + 6 * i, wb);
+  if (sceneBox) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(sceneBox + k, floatToOrdered(wb.lo[k]));
+      atomicMax(sceneBox + 3 + k, floatToOrdered(wb.hi[k]));
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Morton keys
+// -------------------------------------------------------------------------------------------------
+KF_D uint64_t expandBits21(uint64_t v) {
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+__global__ void k_morton(const float* __restrict__ primBox, uint32_t n, const int* __restrict__ sceneBox,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t code = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float lo = orderedToFloat(sceneBox[k]), hi = orderedToFloat(sceneBox[3 + k]);
+    const float c = 0.5f * (primBox[6 * i + k] + primBox[6 * i + 3 + k]);
+    const float ext = hi - lo;
+    float f = ext > 0.0f ? (c - lo) / ext : 0.0f;
+    f = fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+    code |= expandBits21(uint64_t(f)) << (2 - k);
+  }
+  keys[i] = code;
+  vals[i] = i;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable.  Three kernels per pass: per-block digit histograms,
+// a single-block exclusive scan in (digit, block) order, and a stable scatter that ranks keys
+// warp by warp with __match_any_sync.
+// -------------------------------------------------------------------------------------------------
+#define KF_SORT_THREADS 256
+#define KF_SORT_ITEMS 8
+#define KF_SORT_TILE (KF_SORT_THREADS * KF_SORT_ITEMS)
+
+__global__ void k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                            uint32_t* __restrict__ hist /* [256][numBlocks] */, uint32_t numBlocks) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * KF_SORT_TILE;
+#pragma unroll
+  for (int it = 0; it < KF_SORT_ITEMS; it++) {
+    uint32_t i = base + it * KF_SORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * numBlocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// Exclusive scan over hist[256 * numBlocks] by one block (sizes here are small: n / 2048 blocks).
+__global__ void k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
+  __shared__ uint32_t warpSums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < total; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < total ? hist[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < (blockDim.x >> 5) ? warpSums[lane] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warpSums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t prefix = carry + (warp > 0 ? warpSums[warp - 1] : 0u) + x - v;
+    if (i < total) hist[i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
+    __syncthreads();
+  }
+}
+
+__global__ void k_sort_scatter(const uint64_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                               uint64_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t n,
+                               int shift, const uint32_t* __restrict__ hist, uint32_t numBlocks) {
+  __shared__ uint32_t running[256];                       // block offset per digit so far
+  __shared__ uint32_t warpCnt[KF_SORT_THREADS / 32][256]; // per-warp digit counts of this round
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  running[threadIdx.x] = hist[threadIdx.x * numBlocks + blockIdx.x];
+  const uint32_t base = blockIdx.x * KF_SORT_TILE;
+  for (int it = 0; it < KF_SORT_ITEMS; it++) {
+    for (int w = 0; w < KF_SORT_THREADS / 32; w++) warpCnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = base + it * KF_SORT_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    uint64_t key = valid ? keysIn[i] : 0ull;
+    uint32_t digit = valid ? uint32_t((key >> shift) & 0xffu) : 0x100u + lane;  // invalid: unique
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rankInWarp == 0) warpCnt[warp][digit] = __popc(peers);
+    __syncthreads();
+    uint32_t pos = 0;
+    if (valid) {
+      pos = running[digit] + rankInWarp;
+      for (int w = 0; w < warp; w++) pos += warpCnt[w][digit];
+    }
+    __syncthreads();
+    {
+      uint32_t tot = 0;
+      for (int w = 0; w < KF_SORT_THREADS / 32; w++) tot += warpCnt[w][threadIdx.x];
+      running[threadIdx.x] += tot;
+    }
+    if (valid) {
+      keysOut[pos] = key;
+      valsOut[pos] = valsIn[i];
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// LBVH (Karras 2012).  Internal nodes 0..n-2 (root 0); child code >= 0 internal, < 0 leaf ~j.
+// parent[] is indexed [0,n-1) for internal nodes and [n-1, 2n-1) for leaves.
+// -------------------------------------------------------------------------------------------------
+KF_D int lbvhDelta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(uint32_t(i) ^ uint32_t(j));
+  return __clzll((long long)(a ^ b));
+}
+__global__ void k_lbvh_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
+                                 int2* __restrict__ range, int* __restrict__ parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (lbvhDelta(keys, n, i, i + 1) - lbvhDelta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvhDelta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvhDelta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (lbvhDelta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvhDelta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lbvhDelta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const int left = (lo == gamma) ? ~gamma : gamma;
+  const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  children[i] = make_int2(left, right);
+  range[i] = make_int2(lo, hi);
+  if (left >= 0) parent[left] = i; else parent[n - 1 + gamma] = i;
+  if (right >= 0) parent[right] = i; else parent[n - 1 + gamma + 1] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+KF_D Box6 memberBox(int code, const float* __restrict__ nodeBox, const float* __restrict__ primBox,
+                    const uint32_t* __restrict__ vals) {
+  return code >= 0 ? loadBox(nodeBox + 6 * code) : loadBox(primBox + 6 * vals[~code]);
+}
+
+__global__ void k_lbvh_bounds(int n, const int2* __restrict__ children, const int* __restrict__ parent,
+                              const float* __restrict__ primBox, const uint32_t* __restrict__ vals,
+                              float* __restrict__ nodeBox, uint32_t* __restrict__ flags) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int node = parent[n - 1 + j];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(flags + node, 1u) == 0u) return;  // first arrival: the sibling finishes the node
+    const int2 c = children[node];
+    // child boxes were written by other SMs before their fence: read them from L2 (__ldcg),
+    // never through this SM's L1
+    Box6 b = c.x >= 0 ? loadBoxCG(nodeBox + 6 * c.x) : loadBox(primBox + 6 * vals[~c.x]);
+    boxGrow(b, c.y >= 0 ? loadBoxCG(nodeBox + 6 * c.y) : loadBox(primBox + 6 * vals[~c.y]));
+    storeBox(nodeBox + 6 * node, b);
+    node = parent[node];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Wide-node emission
+// -------------------------------------------------------------------------------------------------
+KF_D uint32_t exponentFor(float extent) {
+  // smallest e with extent <= 255 * 2^(e-127); biased exponent byte in [1, 254]
+  const float v = extent * (1.0f / 255.0f);
+  int e = int((__float_as_uint(v) >> 23) & 0xffu) + 1;  // 2^(e-127) > v for normal v
+  if (!(v > 0.0f)) e = 1;
+  return uint32_t(min(max(e, 1), 254));
+}
+
+// Quantises the member boxes of one wide node.  slotBox[s] is ignored where slotUsed bit s is 0.
+KF_D void quantiseNode(Node8& nd, const Box6& nb, const Box6* slotBox, uint32_t slotUsed) {
+  nd.px = nb.lo[0];
+  nd.py = nb.lo[1];
+  nd.pz = nb.lo[2];
+  const uint32_t ex = exponentFor(nb.hi[0] - nb.lo[0]);
+  const uint32_t ey = exponentFor(nb.hi[1] - nb.lo[1]);
+  const uint32_t ez = exponentFor(nb.hi[2] - nb.lo[2]);
+  nd.ex = uint8_t(ex);
+  nd.ey = uint8_t(ey);
+  nd.ez = uint8_t(ez);
+  const float isx = 1.0f / __uint_as_float(ex << 23);
+  const float isy = 1.0f / __uint_as_float(ey << 23);
+  const float isz = 1.0f / __uint_as_float(ez << 23);
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    if (!((slotUsed >> s) & 1u)) {
+      nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
+      nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+      continue;
+    }
+    const Box6& b = slotBox[s];
+    nd.qlox[s] = uint8_t(fminf(fmaxf(floorf((b.lo[0] - nb.lo[0]) * isx), 0.0f), 255.0f));
+    nd.qloy[s] = uint8_t(fminf(fmaxf(floorf((b.lo[1] - nb.lo[1]) * isy), 0.0f), 255.0f));
+    nd.qloz[s] = uint8_t(fminf(fmaxf(floorf((b.lo[2] - nb.lo[2]) * isz), 0.0f), 255.0f));
+    nd.qhix[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[0] - nb.lo[0]) * isx), 0.0f), 255.0f));
+    nd.qhiy[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[1] - nb.lo[1]) * isy), 0.0f), 255.0f));
+    nd.qhiz[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[2] - nb.lo[2]) * isz), 0.0f), 255.0f));
+  }
+}
+
+#define KF_MEMBER_EMPTY 0x7fffffff
+#define KF_LEAF_MAX 3
+
+struct CollapseArgs {
+  int n;                      // primitives
+  const int2* children;       // binary
+  const int2* range;          // binary
+  const float* nodeBox;       // binary internal boxes
+  const float* primBox;       // padded primitive boxes (original order)
+  const uint32_t* vals;       // sorted position -> primitive
+  Node8* outNodes;            // wide nodes
+  uint32_t* outPrim;          // leaf order -> primitive
+  int* wideBinary;            // wide node -> binary internal node it collapses
+  int* wideMembers;           // 8 member codes per wide node (slot order), for refit
+  uint32_t* counters;         // [0] wide nodes allocated, [1] leaf primitives allocated
+};
+
+KF_D int memberCount(int code, const int2* __restrict__ range) {
+  if (code < 0) return 1;
+  const int2 r = range[code];
+  return r.y - r.x + 1;
+}
+KF_D int memberFirst(int code, const int2* __restrict__ range) { return code < 0 ? ~code : range[code].x; }
+
+// One thread per wide node of the current level [lo, hi).
+__global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
+  const uint32_t w = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= hi) return;
+  const int b = a.wideBinary[w];
+  int mem[8];
+  int m = 0;
+  {
+    const int2 c = a.children[b];
+    mem[m++] = c.x;
+    mem[m++] = c.y;
+  }
+  // expand the largest-area expandable member until 8 children
+  while (m < 8) {
+    int best = -1;
+    float bestArea = -1.0f;
+    for (int k = 0; k < m; k++) {
+      if (mem[k] >= 0 && memberCount(mem[k], a.range) > KF_LEAF_MAX) {
+        const float ar = boxArea(loadBox(a.nodeBox + 6 * mem[k]));
+        if (ar > bestArea) { bestArea = ar; best = k; }
+      }
+    }
+    if (best < 0) break;
+    const int2 c = a.children[mem[best]];
+    mem[best] = c.x;
+    mem[m++] = c.y;
+  }
+  const Box6 nb = loadBox(a.nodeBox + 6 * b);
+  float cx = 0.5f * (nb.lo[0] + nb.hi[0]), cy = 0.5f * (nb.lo[1] + nb.hi[1]), cz = 0.5f * (nb.lo[2] + nb.hi[2]);
+  Box6 mb[8];
+  float dx[8], dy[8], dz[8];
+  for (int k = 0; k < m; k++) {
+    mb[k] = memberBox(mem[k], a.nodeBox, a.primBox, a.vals);
+    dx[k] = 0.5f * (mb[k].lo[0] + mb[k].hi[0]) - cx;
+    dy[k] = 0.5f * (mb[k].lo[1] + mb[k].hi[1]) - cy;
+    dz[k] = 0.5f * (mb[k].lo[2] + mb[k].hi[2]) - cz;
+  }
+  // greedy octant slot assignment: slot s prefers the child farthest along (+-1,+-1,+-1)_s
+  int slotOf[8];
+  for (int k = 0; k < 8; k++) slotOf[k] = -1;
+  uint32_t used = 0;
+  for (int round = 0; round < m; round++) {
+    float bestCost = -3.0e38f;
+    int bk = -1, bs = -1;
+    for (int k = 0; k < m; k++) {
+      if (slotOf[k] >= 0) continue;
+      for (int s = 0; s < 8; s++) {
+        if ((used >> s) & 1u) continue;
+        const float cost = ((s & 1) ? dx[k] : -dx[k]) + ((s & 2) ? dy[k] : -dy[k]) + ((s & 4) ? dz[k] : -dz[k]);
+        if (cost > bestCost) { bestCost = cost; bk = k; bs = s; }
+      }
+    }
+    slotOf[bk] = bs;
+    used |= 1u << bs;
+  }
+  int slotMem[8];
+  Box6 slotBox[8];
+  for (int s = 0; s < 8; s++) slotMem[s] = KF_MEMBER_EMPTY;
+  for (int k = 0; k < m; k++) {
+    slotMem[slotOf[k]] = mem[k];
+    slotBox[slotOf[k]] = mb[k];
+  }
+  // count internal children / leaf primitives, allocate
+  uint32_t nInternal = 0, nPrims = 0;
+  for (int s = 0; s < 8; s++) {
+    if (slotMem[s] == KF_MEMBER_EMPTY) continue;
+    const int cnt = memberCount(slotMem[s], a.range);
+    if (cnt > KF_LEAF_MAX) nInternal++; else nPrims += cnt;
+  }
+  const uint32_t childBase = nInternal ? atomicAdd(a.counters + 0, nInternal) : 0u;
+  const uint32_t primBase = nPrims ? atomicAdd(a.counters + 1, nPrims) : 0u;
+  Node8 nd;
+  nd.childBase = childBase;
+  nd.primBase = primBase;
+  uint32_t imask = 0, ci = 0, po = 0;
+  for (int s = 0; s < 8; s++) {
+    const int code = slotMem[s];
+    a.wideMembers[8 * w + s] = code;
+    if (code == KF_MEMBER_EMPTY) { nd.meta[s] = 0; continue; }
+    const int cnt = memberCount(code, a.range);
+    if (cnt > KF_LEAF_MAX) {
+      imask |= 1u << s;
+      nd.meta[s] = uint8_t(0x20u | (24u + s));
+      a.wideBinary[childBase + ci] = code;
+      ci++;
+    } else {
+      const int first = memberFirst(code, a.range);
+      nd.meta[s] = uint8_t((((1u << cnt) - 1u) << 5) | po);
+      for (int q = 0; q < cnt; q++) a.outPrim[primBase + po + q] = a.vals[first + q];
+      po += cnt;
+    }
+  }
+  nd.imask = uint8_t(imask);
+  quantiseNode(nd, nb, slotBox, used);
+  a.outNodes[w] = nd;
+}
+
+// Root for n <= KF_LEAF_MAX primitives: one leaf child holding everything.
+__global__ void k_single_leaf_root(int n, const float* __restrict__ primBox, Node8* outNodes,
+                                   uint32_t* outPrim, int* wideMembers, float* rootBox) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Box6 nb;
+  boxReset(nb);
+  for (int i = 0; i < n; i++) boxGrow(nb, loadBox(primBox + 6 * i));
+  Node8 nd;
+  nd.childBase = 0;
+  nd.primBase = 0;
+  nd.imask = 0;
+  Box6 slotBox[8];
+  for (int s = 0; s < 8; s++) { nd.meta[s] = 0; wideMembers[s] = KF_MEMBER_EMPTY; }
+  nd.meta[0] = uint8_t((((1u << n) - 1u) << 5) | 0u);
+  slotBox[0] = nb;
+  for (int i = 0; i < n; i++) outPrim[i] = uint32_t(i);
+  quantiseNode(nd, nb, slotBox, 1u);
+  outNodes[0] = nd;
+  storeBox(rootBox, nb);
+}
+
+// Refit: re-quantise every wide node from its members' freshly recomputed boxes.
+__global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers,
+                             const float* __restrict__ nodeBox, const float* __restrict__ primBox,
+                             const uint32_t* __restrict__ vals, Node8* nodes, int singleLeafN) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nWide) return;
+  Box6 nb;
+  boxReset(nb);
+  Box6 slotBox[8];
+  uint32_t used = 0;
+  if (singleLeafN > 0) {
+    for (int i = 0; i < singleLeafN; i++) boxGrow(nb, loadBox(primBox + 6 * i));
+    slotBox[0] = nb;
+    used = 1u;
+  } else {
+    for (int s = 0; s < 8; s++) {
+      const int code = wideMembers[8 * w + s];
+      if (code == KF_MEMBER_EMPTY) continue;
+      slotBox[s] = memberBox(code, nodeBox, primBox, vals);
+      boxGrow(nb, slotBox[s]);
+      used |= 1u << s;
+    }
+  }
+  Node8 nd = nodes[w];
+  quantiseNode(nd, nb, slotBox, used);
+  nodes[w] = nd;
+}
+
+// Triangles in leaf order: v0, e1 = v1 - v0, e2 = v2 - v0 (single IEEE subtractions, like the oracle).
+__global__ void k_write_tris(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
+                             const uint32_t* __restrict__ order, uint32_t n, Tri48* __restrict__ out) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t prim = order[k];
+  const float* p0 = verts[idx[3 * prim + 0]].pos;
+  const float* p1 = verts[idx[3 * prim + 1]].pos;
+  const float* p2 = verts[idx[3 * prim + 2]].pos;
+  Tri48 t;
+  t.v0x = p0[0]; t.v0y = p0[1]; t.v0z = p0[2];
+  t.prim = prim;
+  t.e1x = csub(p1[0], p0[0]); t.e1y = csub(p1[1], p0[1]); t.e1z = csub(p1[2], p0[2]); t.pad1 = 0.0f;
+  t.e2x = csub(p2[0], p0[0]); t.e2y = csub(p2[1], p0[1]); t.e2z = csub(p2[2], p0[2]); t.pad2 = 0.0f;
+  out[k] = t;
+}
+
+}  // namespace kf

@@ -1,0 +1,174 @@
+// kf_common.cuh -- shared device/host definitions of the kfrt CUDA core (sm_100a).
+//
+// Arithmetic contract (DESIGN.md "bit-exact hits"): everything that decides WHICH triangle a ray
+// hits and at what t -- camera ray generation, the world->object ray transform, the
+// Moller-Trumbore test, the instance inverse -- is written with the c*() helpers below, which map to
+// __fmul_rn/__fadd_rn/__fsub_rn and therefore are never contracted into FMA, whatever -fmad says.
+// Box tests and shading are free to use FMA: boxes are padded conservatively and radiance parity
+// is toleranced.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kf_rt.h"
+
+#define KF_HD __host__ __device__ __forceinline__
+#define KF_D __device__ __forceinline__
+
+namespace kf {
+
+// ---------------------------------------------------------------------------------------------
+// contract arithmetic (no FMA contraction, IEEE round-to-nearest)
+// ---------------------------------------------------------------------------------------------
+KF_D float cmul(float a, float b) { return __fmul_rn(a, b); }
+KF_D float cadd(float a, float b) { return __fadd_rn(a, b); }
+KF_D float csub(float a, float b) { return __fsub_rn(a, b); }
+KF_D float cdiv(float a, float b) { return __fdiv_rn(a, b); }
+KF_D float csqrt(float a) { return __fsqrt_rn(a); }
+KF_D float cdot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return cadd(cadd(cmul(ax, bx), cmul(ay, by)), cmul(az, bz));
+}
+
+struct V3 {
+  float x, y, z;
+};
+KF_HD V3 mk3(float x, float y, float z) { return V3{x, y, z}; }
+KF_HD V3 mk3(float a) { return V3{a, a, a}; }
+KF_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+KF_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+KF_HD V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+KF_HD V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+KF_HD V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+KF_HD V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+KF_HD V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+KF_HD V3& operator+=(V3& a, V3 b) { a = a + b; return a; }
+KF_HD V3& operator*=(V3& a, V3 b) { a = a * b; return a; }
+KF_HD V3& operator*=(V3& a, float s) { a = a * s; return a; }
+KF_HD bool allEq(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+KF_HD bool anyNe(V3 a, V3 b) { return a.x != b.x || a.y != b.y || a.z != b.z; }
+KF_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+KF_HD V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+KF_D float length(V3 a) { return sqrtf(dot(a, a)); }
+KF_D V3 normalize(V3 a) {
+  float inv = 1.0f / sqrtf(dot(a, a));
+  return a * inv;
+}
+// contract versions (used where bit-exactness with the oracle is required)
+KF_D V3 cnormalize(V3 a) {
+  float inv = cdiv(1.0f, csqrt(cdot3(a.x, a.y, a.z, a.x, a.y, a.z)));
+  return {cmul(a.x, inv), cmul(a.y, inv), cmul(a.z, inv)};
+}
+KF_D V3 ccross(V3 a, V3 b) {
+  return {csub(cmul(a.y, b.z), cmul(a.z, b.y)), csub(cmul(a.z, b.x), cmul(a.x, b.z)),
+          csub(cmul(a.x, b.y), cmul(a.y, b.x))};
+}
+KF_D float cdot(V3 a, V3 b) { return cdot3(a.x, a.y, a.z, b.x, b.y, b.z); }
+KF_D V3 csub3(V3 a, V3 b) { return {csub(a.x, b.x), csub(a.y, b.y), csub(a.z, b.z)}; }
+// column-major 4x4 times (x,y,z,w), summed left to right (oracle mulMat4)
+KF_D void cmulMat4(const float* m, float x, float y, float z, float w, float out[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    out[r] = cadd(cadd(cadd(cmul(m[r], x), cmul(m[4 + r], y)), cmul(m[8 + r], z)), cmul(m[12 + r], w));
+}
+
+KF_D float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+#define KF_PI 3.141592f /* reference base/Random.glsl:1 */
+
+// ---------------------------------------------------------------------------------------------
+// RNG (reference base/Random.glsl:7-39)
+// ---------------------------------------------------------------------------------------------
+KF_HD uint32_t tea(uint32_t val0, uint32_t val1) {
+  uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    s0 += 0x9e3779b9u;
+    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  return v0;
+}
+KF_HD uint32_t lcg(uint32_t& prev) {
+  prev = 1664525u * prev + 1013904223u;
+  return prev & 0x00FFFFFFu;
+}
+// float(lcg)/float(2^24): the 24-bit integer converts exactly and the division by a power of two is
+// exact, so a multiply by 2^-24 is bit-identical to the reference's division.
+KF_HD float rnd(uint32_t& prev) { return float(lcg(prev)) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// Acceleration-structure records
+// ---------------------------------------------------------------------------------------------
+// 8-wide compressed node, 80 bytes = 5 x 16 B loads.  Child boxes are 8-bit offsets from `p` on a
+// per-axis power-of-two grid 2^(e-127); children sit in octant-ordered slots so that traversal
+// order is a bit trick instead of a sort (after Ylitie, Karras, Laine 2017).
+struct __align__(16) Node8 {
+  float px, py, pz;
+  uint8_t ex, ey, ez, imask;  // imask bit i: child slot i is an internal node
+  uint32_t childBase;         // index of first internal child (children are consecutive by slot)
+  uint32_t primBase;          // index of first leaf primitive (triangle / instance-list entry)
+  uint8_t meta[8];            // 0 empty | internal: 0x20|(24+slot) | leaf: unary(count)<<5 | offset
+  uint8_t qlox[8], qloy[8], qloz[8];
+  uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+// Stored triangle, 48 bytes = 3 x 16 B loads: v0 + primitive id, e1 = v1 - v0, e2 = v2 - v0.
+struct __align__(16) Tri48 {
+  float v0x, v0y, v0z;
+  uint32_t prim;
+  float e1x, e1y, e1z, pad1;
+  float e2x, e2y, e2z, pad2;
+};
+static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
+
+// Instance record read when a ray enters a bottom-level structure, 64 bytes = 4 x 16 B loads.
+struct __align__(16) InstRec {
+  float inv[12];          // world->object, 3 rows x 4 columns
+  const Node8* nodes;     // BLAS nodes (root = nodes[0]); NULL when the geometry is hidden/empty
+  const Tri48* tris;      // BLAS triangles in leaf order; bit 0 set == non-opaque geometry
+};
+static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
+
+// Per-geometry shading tables (fetched only at shading time).
+struct GeomRec {
+  const KfrtVertex* verts;
+  const uint32_t* idx;
+  const uint32_t* matIndex;
+  uint32_t nTris;
+  uint32_t flags;  // bit0 opaque, bit1 hideRender
+};
+
+struct TexRec {
+  const uchar4* texels;
+  uint32_t w, h;
+};
+
+struct SceneDev {
+  const Node8* tlasNodes;
+  const uint32_t* tlasInstIdx;  // leaf order -> instance index
+  const InstRec* inst;
+  const KfrtInstance* instSsbo;
+  const GeomRec* geoms;
+  const KfrtMaterial* mats;
+  const TexRec* texs;
+  uint32_t nTex;
+  uint32_t nInst;
+  const uchar4* envFaces;  // 6 faces, size x size each
+  uint32_t envSize;
+  const float* srgbToLinear;  // 256 entries
+  const KfrtDirectionalLight* dl;
+  const KfrtPointLights* pl;
+  const KfrtActiveLights* al;
+};
+
+struct Hit {
+  float t, u, v;
+  int32_t inst, prim;  // -1 on miss
+  uint32_t front;      // 1: front face (det > 0)
+};
+
+}  // namespace kf

@@ -1,0 +1,1115 @@
+// kf_rt.cu -- implementation of the kf_rt.h C ABI: context, uploads, acceleration-structure build
+// sequencing, the path-tracing kernels and the output stage.  sm_100a only; no CPU fallback.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kf_bvh_build.cuh"
+#include "kf_common.cuh"
+#include "kf_shade.cuh"
+#include "kf_traverse.cuh"
+
+using namespace kf;
+
+static_assert(sizeof(KfrtVertex) == 48, "Vertex wire layout");
+static_assert(sizeof(KfrtMaterial) == 80, "NiceMaterialSSBO wire layout");
+static_assert(sizeof(KfrtInstance) == 80, "GeometryInstanceSSBO wire layout");
+static_assert(sizeof(KfrtCamera) == 320, "CameraUBO wire layout");
+static_assert(sizeof(KfrtDirectionalLight) == 32, "DirectionalLightUBO wire layout");
+static_assert(sizeof(KfrtPointLights) == 1024, "PointLightsUBO wire layout");
+static_assert(sizeof(KfrtActiveLights) == 1536, "ActiveLightsUBO wire layout");
+static_assert(sizeof(KfrtPushConstants) == 48, "RtPushConstants wire layout");
+
+// ------------------------------------------------------------------------------------------------
+// small host utilities
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_createError = "";
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct GeomHost {
+  bool present = false, dirty = false, opaque = true, hide = false;
+  uint32_t nVerts = 0, nIdx = 0, nMat = 0;
+  KfrtVertex* verts = nullptr;
+  uint32_t* idx = nullptr;
+  uint32_t* matIndex = nullptr;
+  Node8* nodes = nullptr;
+  Tri48* tris = nullptr;
+  uint32_t nNodes = 0;
+  float box[6] = {0, 0, 0, 0, 0, 0};
+  void freeAll() {
+    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodes); cudaFree(tris);
+    verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; tris = nullptr;
+    present = false;
+    nNodes = 0;
+  }
+};
+
+struct TexHost {
+  uchar4* texels = nullptr;
+  uint32_t w = 0, h = 0;
+};
+
+// Scratch + retained state of one BVH build (the TLAS keeps it for refits).
+struct BuildState {
+  uint32_t n = 0;
+  uint32_t nWide = 0;
+  DevBuf<float> primBox;
+  DevBuf<int> sceneBox;
+  DevBuf<uint64_t> keysA, keysB;
+  DevBuf<uint32_t> valsA, valsB, hist, flags, outPrim, counters;
+  DevBuf<int2> children, range;
+  DevBuf<int> parent, wideBinary, wideMembers;
+  DevBuf<float> nodeBox;
+  DevBuf<Node8> outNodes;
+  uint32_t* sortedVals = nullptr;  // valsA or valsB after the sort
+  void release() {
+    primBox.release(); sceneBox.release(); keysA.release(); keysB.release(); valsA.release();
+    valsB.release(); hist.release(); flags.release(); outPrim.release(); counters.release();
+    children.release(); range.release(); parent.release(); wideBinary.release();
+    wideMembers.release(); nodeBox.release(); outNodes.release();
+  }
+};
+
+}  // namespace
+
+struct KfrtContext {
+  int device = 0;
+  cudaStream_t ownStream = nullptr, stream = nullptr;
+  std::string err;
+  uint32_t maxGeometry = 128, maxInstances = 256, maxTextures = 128, maxMaterials = 256;
+
+  std::vector<GeomHost> geoms;
+  DevBuf<GeomRec> geomTable;
+  DevBuf<BlasInfo> blasInfo;
+  bool tablesDirty = true;
+
+  DevBuf<KfrtMaterial> mats;
+  uint32_t nMats = 0;
+  std::vector<TexHost> texs;
+  DevBuf<TexRec> texTable;
+  bool texDirty = true;
+  DevBuf<uchar4> env;
+  uint32_t envSize = 0;
+  DevBuf<KfrtDirectionalLight> dl;
+  DevBuf<KfrtPointLights> pl;
+  DevBuf<KfrtActiveLights> al;
+  uint32_t nLightSlots = 0;
+  DevBuf<float> srgbToLinear, srgbThreshold;
+
+  std::vector<KfrtInstance> instHost;
+  DevBuf<KfrtInstance> instDev;
+  DevBuf<InstRec> instRec;
+  DevBuf<uint32_t> tlasInstIdx;
+  DevBuf<Node8> tlasNodes;
+  uint32_t nTlasNodes = 0;
+  bool blasBuilt = false, tlasBuilt = false;
+  BuildState blasBuild, tlasBuild;
+
+  // outputs
+  uint32_t nCams = 0, width = 0, height = 0;
+  DevBuf<KfrtCamera> cams;
+  DevBuf<float4> sum, rgba, albedo, normal;
+  DevBuf<int2> hitIds;
+  DevBuf<float> hitT, depth;
+  DevBuf<uchar4> bgra;
+  DevBuf<unsigned long long> counters;
+  KfrtPushConstants lastPc{};
+  bool rendered = false;
+  int detail = 0;
+  uint64_t launches = 0;
+  KfrtCounters lastCounters{};
+};
+
+#define KF_FAIL(ctx, code, msg)  \
+  do {                           \
+    (ctx)->err = (msg);          \
+    return (code);               \
+  } while (0)
+
+#define KF_CUDA(ctx, expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                         \
+      return KFRT_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+#define KF_CHECK_CTX(ctx) \
+  if (!(ctx)) return KFRT_ERR_INVALID
+
+static inline unsigned gridFor(size_t n, unsigned block) { return unsigned((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------
+// BVH build sequencing
+// ------------------------------------------------------------------------------------------------
+static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
+  const uint32_t numBlocks = gridFor(n, KF_SORT_TILE);
+  KF_CUDA(ctx, st.hist.ensure(size_t(256) * numBlocks));
+  uint64_t *kin = st.keysA.p, *kout = st.keysB.p;
+  uint32_t *vin = st.valsA.p, *vout = st.valsB.p;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = pass * 8;
+    k_sort_hist<<<numBlocks, KF_SORT_THREADS, 0, ctx->stream>>>(kin, n, shift, st.hist.p, numBlocks);
+    k_sort_scan<<<1, 1024, 0, ctx->stream>>>(st.hist.p, 256u * numBlocks);
+    k_sort_scatter<<<numBlocks, KF_SORT_THREADS, 0, ctx->stream>>>(kin, vin, kout, vout, n, shift, st.hist.p,
+                                                                   numBlocks);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  // 8 passes: data is back in A
+  st.sortedVals = vin;
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+// Builds the wide BVH over st.primBox[0..n) (already filled, with st.sceneBox).  On return
+// st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
+static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n) {
+  st.n = n;
+  KF_CUDA(ctx, st.outNodes.ensure(std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.outPrim.ensure(n));
+  KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.wideBinary.ensure(std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.counters.ensure(2));
+  KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
+  if (n <= KF_LEAF_MAX) {
+    k_single_leaf_root<<<1, 32, 0, ctx->stream>>>(int(n), st.primBox.p, st.outNodes.p, st.outPrim.p,
+                                                  st.wideMembers.p, st.nodeBox.p);
+    st.nWide = 1;
+    KF_CUDA(ctx, cudaGetLastError());
+    return KFRT_OK;
+  }
+  KF_CUDA(ctx, st.keysA.ensure(n));
+  KF_CUDA(ctx, st.keysB.ensure(n));
+  KF_CUDA(ctx, st.valsA.ensure(n));
+  KF_CUDA(ctx, st.valsB.ensure(n));
+  KF_CUDA(ctx, st.children.ensure(n));
+  KF_CUDA(ctx, st.range.ensure(n));
+  KF_CUDA(ctx, st.parent.ensure(size_t(2) * n));
+  KF_CUDA(ctx, st.flags.ensure(n));
+  k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
+  int rc = radixSort(ctx, st, n);
+  if (rc) return rc;
+  k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
+                                                                 st.range.p, st.parent.p);
+  KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
+  k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
+                                                          st.sortedVals, st.nodeBox.p, st.flags.p);
+  // collapse, one launch per level of the wide tree
+  const uint32_t init[2] = {1u, 0u};
+  const int zero = 0;
+  KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.wideBinary.p, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CollapseArgs a;
+  a.n = int(n);
+  a.children = st.children.p;
+  a.range = st.range.p;
+  a.nodeBox = st.nodeBox.p;
+  a.primBox = st.primBox.p;
+  a.vals = st.sortedVals;
+  a.outNodes = st.outNodes.p;
+  a.outPrim = st.outPrim.p;
+  a.wideBinary = st.wideBinary.p;
+  a.wideMembers = st.wideMembers.p;
+  a.counters = st.counters.p;
+  uint32_t lo = 0, hi = 1;
+  while (lo < hi) {
+    k_collapse_level<<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
+    uint32_t cnt = 0;
+    KF_CUDA(ctx, cudaMemcpyAsync(&cnt, st.counters.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lo = hi;
+    hi = cnt;
+    if (hi > n) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
+  }
+  st.nWide = hi;
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+static void orderedBoxToFloat(const int* ib, float* out) {
+  for (int k = 0; k < 6; k++) {
+    int i = ib[k];
+    i = i >= 0 ? i : i ^ 0x7fffffff;
+    std::memcpy(out + k, &i, 4);
+  }
+}
+
+static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
+  cudaFree(g.nodes);
+  cudaFree(g.tris);
+  g.nodes = nullptr;
+  g.tris = nullptr;
+  g.nNodes = 0;
+  const uint32_t nTris = g.nIdx / 3;
+  if (nTris == 0 || g.hide) return KFRT_OK;
+  BuildState& st = ctx->blasBuild;
+  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * nTris));
+  KF_CUDA(ctx, st.sceneBox.ensure(6));
+  k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
+  k_tri_boxes<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, nTris, st.primBox.p, st.sceneBox.p);
+  int rc = buildWideBvh(ctx, st, nTris);
+  if (rc) return rc;
+  KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.nodes), sizeof(Node8) * st.nWide));
+  KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris));
+  KF_CUDA(ctx, cudaMemcpyAsync(g.nodes, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+  k_write_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, st.outPrim.p, nTris, g.tris);
+  int ib[6];
+  KF_CUDA(ctx, cudaMemcpyAsync(ib, st.sceneBox.p, sizeof(ib), cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  orderedBoxToFloat(ib, g.box);
+  g.nNodes = st.nWide;
+  return KFRT_OK;
+}
+
+static int uploadTables(KfrtContext* ctx) {
+  const size_t n = ctx->geoms.size();
+  std::vector<GeomRec> recs(std::max<size_t>(n, 1));
+  std::vector<BlasInfo> infos(std::max<size_t>(n, 1));
+  for (size_t i = 0; i < n; i++) {
+    const GeomHost& g = ctx->geoms[i];
+    recs[i].verts = g.verts;
+    recs[i].idx = g.idx;
+    recs[i].matIndex = g.matIndex;
+    recs[i].nTris = g.nIdx / 3;
+    recs[i].flags = (g.opaque ? 1u : 0u) | (g.hide ? 2u : 0u);
+    infos[i].nodes = g.nodes;
+    infos[i].tris = g.tris;
+    std::memcpy(infos[i].box, g.box, sizeof(g.box));
+    infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u);
+    infos[i].pad = 0;
+  }
+  KF_CUDA(ctx, ctx->geomTable.ensure(recs.size()));
+  KF_CUDA(ctx, ctx->blasInfo.ensure(infos.size()));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->geomTable.p, recs.data(), sizeof(GeomRec) * recs.size(),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->blasInfo.p, infos.data(), sizeof(BlasInfo) * infos.size(),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->tablesDirty = false;
+  return KFRT_OK;
+}
+
+static int uploadTexTable(KfrtContext* ctx) {
+  std::vector<TexRec> recs(std::max<size_t>(ctx->texs.size(), 1));
+  for (size_t i = 0; i < ctx->texs.size(); i++) {
+    recs[i].texels = ctx->texs[i].texels;
+    recs[i].w = ctx->texs[i].w;
+    recs[i].h = ctx->texs[i].h;
+  }
+  if (ctx->texs.empty()) recs[0] = TexRec{nullptr, 0, 0};
+  KF_CUDA(ctx, ctx->texTable.ensure(recs.size()));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->texTable.p, recs.data(), sizeof(TexRec) * recs.size(),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->texDirty = false;
+  return KFRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Render kernels
+// ------------------------------------------------------------------------------------------------
+struct RenderArgs {
+  SceneDev sc;
+  const KfrtCamera* cams;
+  uint32_t nCams, w, h;
+  KfrtPushConstants pc;
+  uint32_t s0, s1, clockBase;
+  float4* sum;
+  float4* albedo;
+  float4* normal;
+  int2* hitIds;
+  float* hitT;
+  float* depth;
+  unsigned long long* counters;  // [0] paths [1] ext [2] shadow [3] hits [4] nodes [5] tris [6] insts [7] tex
+};
+
+KF_D unsigned long long warpSum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Camera ray of one sample (reference PathTrace.rgen:35-56), contract arithmetic: the primary-ray
+// bits must equal the oracle's so that 1-spp hit buffers can be compared bit-exactly.
+KF_D void cameraRay(const KfrtCamera* __restrict__ cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
+                    uint32_t& pixelSeed, uint32_t& raySeed, V3& o, V3& d) {
+  const float jx = rnd(pixelSeed);
+  const float jy = rnd(pixelSeed);
+  const float px = cadd(float(x), jx), py = cadd(float(y), jy);
+  const float nx = cdiv(px, float(w)), ny = cdiv(py, float(h));
+  const float dx = csub(cmul(nx, 2.0f), 1.0f), dy = csub(cmul(ny, 2.0f), 1.0f);
+  const float aperture = cam->position[3];
+  const float focus = cam->front[3];
+  float ox, oy;
+  diskSampling(raySeed, ox, oy);
+  ox = cmul(cdiv(aperture, 2.0f), ox);
+  oy = cmul(cdiv(aperture, 2.0f), oy);
+  float target[4], origin[4], direction[4];
+  cmulMat4(cam->projectionInverse, dx, dy, 1.0f, 1.0f, target);
+  if (aperture > 0.0f) {
+    cmulMat4(cam->viewInverse, ox, oy, 0.0f, 1.0f, origin);
+    const V3 t = mk3(csub(cmul(target[0], focus), ox), csub(cmul(target[1], focus), oy),
+                     csub(cmul(target[2], focus), 0.0f));
+    const V3 dd = cnormalize(t);
+    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
+  } else {
+    cmulMat4(cam->viewInverse, 0.0f, 0.0f, 0.0f, 1.0f, origin);
+    const V3 dd = cnormalize(mk3(target[0], target[1], target[2]));
+    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
+  }
+  o = mk3(origin[0], origin[1], origin[2]);
+  d = mk3(direction[0], direction[1], direction[2]);
+}
+
+// One thread per pixel: the whole of PathTrace.rgen:19-141 with traversal and shading inlined.
+// (Round-1 baseline scheduler; the wavefront scheduler reuses the same device functions.)
+template <bool DETAIL>
+__global__ void __launch_bounds__(64) k_render_mega(RenderArgs a) {
+  const uint32_t x = blockIdx.x * 8 + (threadIdx.x & 7);
+  const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 3);
+  const uint32_t c = blockIdx.z;
+  unsigned long long nExt = 0, nSh = 0, nHit = 0, nTex = 0;
+  TravCounters tc{0, 0, 0};
+  unsigned long long nNodes = 0, nTris = 0, nInsts = 0;
+  if (x < a.w && y < a.h) {
+    const KfrtCamera* cam = a.cams + c;
+    const KfrtPushConstants& pc = a.pc;
+    const uint32_t mapping = y * a.w + x;
+    uint32_t seed = tea(mapping, a.clockBase);
+    for (uint32_t k = 0; k < 2 * a.s0; k++) lcg(seed);
+    V3 colors = mk3(0.0f), albedoOut = mk3(0.0f), normalOut = mk3(0.0f);
+    int32_t hitInst = -1, hitPrim = -1;
+    float hitT = 0.0f, hitDepth = 0.0f;
+    for (uint32_t i = a.s0; i < a.s1; ++i) {
+      uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
+      V3 ro, rd;
+      cameraRay(cam, x, y, a.w, a.h, seed, raySeed, ro, rd);
+      V3 weight = mk3(1.0f), color = mk3(0.0f);
+      V3 rayWeight = mk3(0.0f);  // ray.weight persists across bounces (stale on miss / emissive)
+      for (uint32_t depth = 0; depth <= pc.maxPathDepth; ++depth) {
+        Hit hit;
+        nExt++;
+        const bool found = traverse<false, DETAIL>(a.sc, ro, rd, 0.001f, 10000.0f, raySeed, hit, tc);
+        if (i == 0 && depth == 0 && found) {
+          hitInst = hit.inst;
+          hitPrim = hit.prim;
+          hitT = hit.t;
+          // view-space depth: -(view * P).z with P = o + d * t (contract arithmetic)
+          const float Px = cadd(ro.x, cmul(rd.x, hit.t)), Py = cadd(ro.y, cmul(rd.y, hit.t)),
+                      Pz = cadd(ro.z, cmul(rd.z, hit.t));
+          const float* vm = cam->view;
+          hitDepth = -cadd(cadd(cadd(cmul(vm[2], Px), cmul(vm[6], Py)), cmul(vm[10], Pz)), vm[14]);
+        }
+        V3 emission = mk3(0.0f), shadowColor = mk3(0.0f), albedo = mk3(0.0f), N = mk3(0.0f);
+        bool pathEnds = false;
+        uint32_t tex = 0;
+        if (found) {
+          nHit++;
+          Surface sf;
+          V3 L, w;
+          if (shadeSurface(a.sc, hit, ro, rd, raySeed, sf, L, w, albedo, emission, tex)) {
+            // next-event estimation, lights in reference order (rchit:457-460)
+            int k = 0;
+            V3 Ls, le;
+            float maxDist;
+            while (nextLight(a.sc, sf, raySeed, k, Ls, maxDist, le, tex)) {
+              Hit sh;
+              nSh++;
+              const bool occluded = traverse<true, DETAIL>(a.sc, sf.worldPos, Ls, 0.001f, maxDist, 0u, sh, tc);
+              if (!occluded) shadowColor += calcDirect(sf, Ls, le, raySeed);
+              k++;
+            }
+            ro = sf.worldPos;
+            rd = L;
+            rayWeight = w;
+            N = sf.N;
+          } else {
+            pathEnds = true;  // emissive surface: ray.depth = maxPathDepth + 1 (rchit:330-334)
+          }
+        } else {
+          emission = shadeMiss(a.sc, pc, rd, tex);
+          pathEnds = true;  // rmiss:30
+        }
+        nTex += tex;
+        color += emission * weight;
+        weight *= rayWeight;
+        color += shadowColor * weight;
+        if (i == 0 && depth == 0 && !pathEnds) {  // rgen:114-117 (ray.depth is still 0 only for surfaces)
+          albedoOut = albedo;
+          normalOut = N;
+        }
+        if (allEq(weight, mk3(0.0f))) break;
+        // Russian roulette (rgen:124-138); after a miss/emissive hit ray.depth = maxPathDepth + 1,
+        // the draw below is then unobservable (the stream is re-seeded per sample), so skip it.
+        if (pathEnds) break;
+        if (pc.russianRoulette && depth >= pc.russianRouletteMinBounces) {
+          const float p = fmaxf(weight.x, fmaxf(weight.y, weight.z));
+          const float r = rnd(raySeed);
+          if (r > p) break;
+          weight *= 1.0f / p;
+        }
+      }
+      colors += color;
+    }
+    const size_t pi = (size_t(c) * a.h + y) * a.w + x;
+    a.sum[pi] = make_float4(colors.x, colors.y, colors.z, float(a.s1 - a.s0));
+    if (a.s0 == 0) {
+      a.albedo[pi] = make_float4(albedoOut.x, albedoOut.y, albedoOut.z, 1.0f);
+      a.normal[pi] = make_float4(normalOut.x, normalOut.y, normalOut.z, 1.0f);
+      a.hitIds[pi] = make_int2(hitInst, hitPrim);
+      a.hitT[pi] = hitT;
+      a.depth[pi] = hitDepth;
+    }
+    if (DETAIL) { nNodes = tc.nodes; nTris = tc.tris; nInsts = tc.insts; }
+  }
+  nExt = warpSum(nExt);
+  nSh = warpSum(nSh);
+  nHit = warpSum(nHit);
+  if (DETAIL) {
+    nNodes = warpSum(nNodes);
+    nTris = warpSum(nTris);
+    nInsts = warpSum(nInsts);
+    nTex = warpSum(nTex);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(a.counters + 1, nExt);
+    atomicAdd(a.counters + 2, nSh);
+    atomicAdd(a.counters + 3, nHit);
+    if (DETAIL) {
+      atomicAdd(a.counters + 4, nNodes);
+      atomicAdd(a.counters + 5, nTris);
+      atomicAdd(a.counters + 6, nInsts);
+      atomicAdd(a.counters + 7, nTex);
+    }
+  }
+}
+
+// Accumulate + encode (reference PathTrace.rgen:143-163, PostProcessing.frag:11-18 into a
+// B8G8R8A8Srgb attachment).  The 8-bit sRGB code is found by binary search over the 255 linear
+// thresholds so that the bytes are bit-exact with the oracle (no pow on the device).
+KF_D unsigned char encodeSrgb8(const float* __restrict__ thr, float c) {
+  if (!(c > 0.0f)) return 0;
+  int lo = 0, hi = 255;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c >= __ldg(thr + mid)) lo = mid + 1; else hi = mid;
+  }
+  return (unsigned char)lo;
+}
+__global__ void k_resolve(const float4* __restrict__ sum, float4* __restrict__ rgba, uchar4* __restrict__ bgra,
+                          size_t nPixels, uint32_t spp, int frameCount, const float* __restrict__ thr) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nPixels) return;
+  const float4 s = sum[i];
+  float fc[3] = {cdiv(s.x, float(spp)), cdiv(s.y, float(spp)), cdiv(s.z, float(spp))};
+  if (frameCount > 0) {
+    const float4 old = rgba[i];
+    const float al = cdiv(1.0f, float(frameCount + 1));
+    const float om = csub(1.0f, al);
+    fc[0] = cadd(cmul(old.x, om), cmul(fc[0], al));
+    fc[1] = cadd(cmul(old.y, om), cmul(fc[1], al));
+    fc[2] = cadd(cmul(old.z, om), cmul(fc[2], al));
+  }
+  rgba[i] = make_float4(fc[0], fc[1], fc[2], 1.0f);
+  bgra[i] = make_uchar4(encodeSrgb8(thr, fc[2]), encodeSrgb8(thr, fc[1]), encodeSrgb8(thr, fc[0]), 255);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* kfrtVersion(void) { return "kuafu_b200 kfrt 0.1 (sm_100a)"; }
+
+const char* kfrtLastError(const KfrtContext* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
+  if (!out) return KFRT_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_createError = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                    " (kfrt has no CPU fallback)";
+    return KFRT_ERR_CUDA;
+  }
+  if (deviceOrdinal < 0 || deviceOrdinal >= count) {
+    g_createError = "device ordinal out of range";
+    return KFRT_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, deviceOrdinal);
+  if (e != cudaSuccess) {
+    g_createError = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return KFRT_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_createError = "kfrt is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                    std::to_string(prop.minor);
+    return KFRT_ERR_CUDA;
+  }
+  e = cudaSetDevice(deviceOrdinal);
+  if (e != cudaSuccess) {
+    g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return KFRT_ERR_CUDA;
+  }
+  KfrtContext* ctx = new KfrtContext();
+  ctx->device = deviceOrdinal;
+  e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_createError = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete ctx;
+    return KFRT_ERR_CUDA;
+  }
+  ctx->stream = ctx->ownStream;
+  // sRGB decode table and encode thresholds (same double-precision formulas as the oracle)
+  float lut[256], thr[255];
+  for (int i = 0; i < 256; i++) {
+    const double c = i / 255.0;
+    lut[i] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+  }
+  for (int k = 0; k < 255; k++) {
+    const double c = (k + 0.5) / 255.0;
+    thr[k] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+  }
+  bool ok = ctx->srgbToLinear.ensure(256) == cudaSuccess && ctx->srgbThreshold.ensure(255) == cudaSuccess &&
+            ctx->dl.ensure(1) == cudaSuccess && ctx->pl.ensure(1) == cudaSuccess && ctx->al.ensure(1) == cudaSuccess &&
+            ctx->counters.ensure(16) == cudaSuccess;
+  if (ok) {
+    ok = cudaMemcpy(ctx->srgbToLinear.p, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(ctx->srgbThreshold.p, thr, sizeof(thr), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemset(ctx->dl.p, 0, sizeof(KfrtDirectionalLight)) == cudaSuccess &&
+         cudaMemset(ctx->pl.p, 0, sizeof(KfrtPointLights)) == cudaSuccess &&
+         cudaMemset(ctx->al.p, 0, sizeof(KfrtActiveLights)) == cudaSuccess;
+  }
+  if (!ok) {
+    g_createError = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    kfrtDestroy(ctx);
+    return KFRT_ERR_CUDA;
+  }
+  *out = ctx;
+  return KFRT_OK;
+}
+
+int kfrtDestroy(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& g : ctx->geoms) g.freeAll();
+  for (auto& t : ctx->texs) cudaFree(t.texels);
+  ctx->geomTable.release(); ctx->blasInfo.release(); ctx->mats.release(); ctx->texTable.release();
+  ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release();
+  ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
+  ctx->instRec.release(); ctx->tlasInstIdx.release(); ctx->tlasNodes.release();
+  ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
+  ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
+  ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
+  if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+  return KFRT_OK;
+}
+
+int kfrtSetStream(KfrtContext* ctx, void* cudaStream) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : ctx->ownStream;
+  return KFRT_OK;
+}
+
+int kfrtSynchronize(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KFRT_OK;
+}
+
+int kfrtSetLimits(KfrtContext* ctx, uint32_t maxGeometry, uint32_t maxInstances, uint32_t maxTextures,
+                  uint32_t maxMaterials) {
+  KF_CHECK_CTX(ctx);
+  if (!maxGeometry || !maxInstances || !maxTextures || !maxMaterials)
+    KF_FAIL(ctx, KFRT_ERR_INVALID, "limits must be non-zero");
+  ctx->maxGeometry = maxGeometry;
+  ctx->maxInstances = maxInstances;
+  ctx->maxTextures = maxTextures;
+  ctx->maxMaterials = maxMaterials;
+  return KFRT_OK;
+}
+
+int kfrtUploadGeometry(KfrtContext* ctx, uint32_t geometryIndex, const KfrtVertex* vertices, uint32_t nVertices,
+                       const uint32_t* indices, uint32_t nIndices, const uint32_t* matIndex, uint32_t nMatIndex,
+                       int opaque, int hideRender) {
+  KF_CHECK_CTX(ctx);
+  if (geometryIndex >= ctx->maxGeometry) KF_FAIL(ctx, KFRT_ERR_LIMIT, "geometry index exceeds the geometry limit");
+  if (nIndices % 3 != 0) KF_FAIL(ctx, KFRT_ERR_INVALID, "index count must be a multiple of 3");
+  if (nIndices && (!vertices || !indices || !matIndex)) KF_FAIL(ctx, KFRT_ERR_INVALID, "null geometry buffer");
+  if (nMatIndex < nIndices / 3) KF_FAIL(ctx, KFRT_ERR_INVALID, "matIndex shorter than the primitive count");
+  for (uint32_t i = 0; i < nIndices; i++)
+    if (indices[i] >= nVertices) KF_FAIL(ctx, KFRT_ERR_INVALID, "vertex index out of range");
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->geoms.size() <= geometryIndex) ctx->geoms.resize(geometryIndex + 1);
+  GeomHost& g = ctx->geoms[geometryIndex];
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  g.freeAll();
+  g.nVerts = nVertices;
+  g.nIdx = nIndices;
+  g.nMat = nMatIndex;
+  g.opaque = opaque != 0;
+  g.hide = hideRender != 0;
+  if (nIndices) {
+    KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.verts), sizeof(KfrtVertex) * nVertices));
+    KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.idx), sizeof(uint32_t) * nIndices));
+    KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.matIndex), sizeof(uint32_t) * nMatIndex));
+    KF_CUDA(ctx, cudaMemcpyAsync(g.verts, vertices, sizeof(KfrtVertex) * nVertices, cudaMemcpyHostToDevice, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(g.idx, indices, sizeof(uint32_t) * nIndices, cudaMemcpyHostToDevice, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(g.matIndex, matIndex, sizeof(uint32_t) * nMatIndex, cudaMemcpyHostToDevice, ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  g.present = true;
+  g.dirty = true;
+  ctx->tablesDirty = true;
+  ctx->tlasBuilt = false;
+  return KFRT_OK;
+}
+
+int kfrtClearGeometries(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& g : ctx->geoms) g.freeAll();
+  ctx->geoms.clear();
+  ctx->tablesDirty = true;
+  ctx->blasBuilt = false;
+  ctx->tlasBuilt = false;
+  return KFRT_OK;
+}
+
+int kfrtUploadMaterials(KfrtContext* ctx, const KfrtMaterial* materials, uint32_t n) {
+  KF_CHECK_CTX(ctx);
+  if (n > ctx->maxMaterials) KF_FAIL(ctx, KFRT_ERR_LIMIT, "material count exceeds the material limit");
+  if (n && !materials) KF_FAIL(ctx, KFRT_ERR_INVALID, "null materials");
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  KF_CUDA(ctx, ctx->mats.ensure(std::max<uint32_t>(n, 1)));
+  if (n) KF_CUDA(ctx, cudaMemcpyAsync(ctx->mats.p, materials, sizeof(KfrtMaterial) * n, cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nMats = n;
+  return KFRT_OK;
+}
+
+int kfrtUploadTexture(KfrtContext* ctx, uint32_t textureIndex, const uint8_t* rgba8, uint32_t width, uint32_t height) {
+  KF_CHECK_CTX(ctx);
+  if (textureIndex >= ctx->maxTextures) KF_FAIL(ctx, KFRT_ERR_LIMIT, "texture index exceeds the texture limit");
+  if (!rgba8 || !width || !height) KF_FAIL(ctx, KFRT_ERR_INVALID, "empty texture");
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->texs.size() <= textureIndex) ctx->texs.resize(textureIndex + 1);
+  TexHost& t = ctx->texs[textureIndex];
+  cudaFree(t.texels);
+  t.texels = nullptr;
+  KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&t.texels), size_t(width) * height * 4));
+  KF_CUDA(ctx, cudaMemcpyAsync(t.texels, rgba8, size_t(width) * height * 4, cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  t.w = width;
+  t.h = height;
+  ctx->texDirty = true;
+  return KFRT_OK;
+}
+
+int kfrtSetEnvironmentCube(KfrtContext* ctx, const uint8_t* const faces[6], uint32_t size) {
+  KF_CHECK_CTX(ctx);
+  if (!faces || !size) KF_FAIL(ctx, KFRT_ERR_INVALID, "empty cube map");
+  for (int f = 0; f < 6; f++)
+    if (!faces[f]) KF_FAIL(ctx, KFRT_ERR_INVALID, "null cube face");
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const size_t faceTexels = size_t(size) * size;
+  KF_CUDA(ctx, ctx->env.ensure(6 * faceTexels));
+  for (int f = 0; f < 6; f++)
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->env.p + f * faceTexels, faces[f], faceTexels * 4, cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->envSize = size;
+  return KFRT_OK;
+}
+
+int kfrtClearEnvironment(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  ctx->envSize = 0;
+  return KFRT_OK;
+}
+
+int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, const KfrtPointLights* points,
+                  const KfrtActiveLights* actives) {
+  KF_CHECK_CTX(ctx);
+  KfrtDirectionalLight d{};
+  KfrtPointLights p{};
+  KfrtActiveLights a{};
+  if (directional) d = *directional;
+  if (points) p = *points;
+  if (actives) a = *actives;
+  uint32_t slots = 0;
+  if (d.rgbs[0] * d.rgbs[3] != 0 || d.rgbs[1] * d.rgbs[3] != 0 || d.rgbs[2] * d.rgbs[3] != 0) slots++;
+  for (int i = 0; i < KFRT_MAX_POINT_LIGHTS; i++)
+    if (p.rgbs[i][3] > 0) slots++;
+  for (int i = 0; i < KFRT_MAX_ACTIVE_LIGHTS; i++)
+    if (a.front[i][3] > 0) slots++;
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->dl.p, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->pl.p, &p, sizeof(p), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->al.p, &a, sizeof(a), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nLightSlots = slots;
+  return KFRT_OK;
+}
+
+int kfrtBuildBlas(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (auto& g : ctx->geoms) {
+    if (!g.present || !g.dirty) continue;
+    int rc = buildOneBlas(ctx, g);
+    if (rc) return rc;
+    g.dirty = false;
+  }
+  ctx->blasBuilt = true;
+  ctx->tablesDirty = true;
+  ctx->tlasBuilt = false;
+  return KFRT_OK;
+}
+
+int kfrtSetInstances(KfrtContext* ctx, const KfrtInstance* instances, uint32_t n) {
+  KF_CHECK_CTX(ctx);
+  if (n > ctx->maxInstances) KF_FAIL(ctx, KFRT_ERR_LIMIT, "instance count exceeds the instance limit");
+  if (n && !instances) KF_FAIL(ctx, KFRT_ERR_INVALID, "null instances");
+  for (uint32_t i = 0; i < n; i++)
+    if (instances[i].geometryIndex >= ctx->geoms.size() || !ctx->geoms[instances[i].geometryIndex].present)
+      KF_FAIL(ctx, KFRT_ERR_INVALID,
+              "geometry index is out of bounds (hint for SAPIEN users: are you creating two active renders?)");
+  ctx->instHost.assign(instances, instances + n);
+  ctx->tlasBuilt = false;
+  return KFRT_OK;
+}
+
+static int instanceSetup(KfrtContext* ctx, bool withSceneBox) {
+  const uint32_t n = uint32_t(ctx->instHost.size());
+  BuildState& st = ctx->tlasBuild;
+  KF_CUDA(ctx, ctx->instDev.ensure(std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, ctx->instRec.ensure(std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.sceneBox.ensure(6));
+  if (n == 0) return KFRT_OK;
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->instDev.p, ctx->instHost.data(), sizeof(KfrtInstance) * n,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  if (withSceneBox) k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
+  k_instance_setup<<<gridFor(n, 128), 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p,
+                                                             uint32_t(ctx->geoms.size()), ctx->instRec.p,
+                                                             st.primBox.p, withSceneBox ? st.sceneBox.p : nullptr);
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+int kfrtBuildTlas(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->blasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtBuildTlas before kfrtBuildBlas");
+  for (auto& g : ctx->geoms)
+    if (g.present && g.dirty) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "geometry uploaded after the last kfrtBuildBlas");
+  if (ctx->tablesDirty) {
+    int rc = uploadTables(ctx);
+    if (rc) return rc;
+  }
+  const uint32_t n = uint32_t(ctx->instHost.size());
+  int rc = instanceSetup(ctx, true);
+  if (rc) return rc;
+  if (n == 0) {
+    ctx->nTlasNodes = 0;
+    ctx->tlasBuilt = true;
+    return KFRT_OK;
+  }
+  BuildState& st = ctx->tlasBuild;
+  rc = buildWideBvh(ctx, st, n);
+  if (rc) return rc;
+  KF_CUDA(ctx, ctx->tlasNodes.ensure(st.nWide));
+  KF_CUDA(ctx, ctx->tlasInstIdx.ensure(n));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasNodes.p, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasInstIdx.p, st.outPrim.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nTlasNodes = st.nWide;
+  ctx->tlasBuilt = true;
+  return KFRT_OK;
+}
+
+int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->tlasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtRefitTlas before kfrtBuildTlas");
+  if (n != ctx->instHost.size()) KF_FAIL(ctx, KFRT_ERR_INVALID, "transform count differs from the instance count");
+  if (n == 0) return KFRT_OK;
+  if (!transforms) KF_FAIL(ctx, KFRT_ERR_INVALID, "null transforms");
+  for (uint32_t i = 0; i < n; i++) std::memcpy(ctx->instHost[i].transform, transforms + 16 * i, 64);
+  int rc = instanceSetup(ctx, false);
+  if (rc) return rc;
+  BuildState& st = ctx->tlasBuild;
+  if (n > KF_LEAF_MAX) {
+    KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
+    k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
+                                                            st.sortedVals, st.nodeBox.p, st.flags.p);
+    k_requantise<<<gridFor(st.nWide, 128), 128, 0, ctx->stream>>>(st.nWide, st.wideMembers.p, st.nodeBox.p,
+                                                                  st.primBox.p, st.sortedVals, ctx->tlasNodes.p, 0);
+  } else {
+    k_requantise<<<1, 32, 0, ctx->stream>>>(1u, st.wideMembers.p, st.nodeBox.p, st.primBox.p, st.sortedVals,
+                                            ctx->tlasNodes.p, int(n));
+  }
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
+  KF_CHECK_CTX(ctx);
+  if (!out) KF_FAIL(ctx, KFRT_ERR_INVALID, "null stats");
+  std::memset(out, 0, sizeof(*out));
+  for (auto& g : ctx->geoms) {
+    if (!g.present) continue;
+    out->blasCount++;
+    out->triangleCount += g.nIdx / 3;
+    out->blasNodeCount += g.nNodes;
+  }
+  out->instanceCount = uint32_t(ctx->instHost.size());
+  for (auto& in : ctx->instHost)
+    if (in.geometryIndex < ctx->geoms.size()) out->instancedTriangles += ctx->geoms[in.geometryIndex].nIdx / 3;
+  out->tlasNodeCount = ctx->nTlasNodes;
+  out->nodeBytes = sizeof(Node8);
+  out->triangleBytes = sizeof(Tri48);
+  out->instanceBytes = sizeof(InstRec);
+  return KFRT_OK;
+}
+
+static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t h) {
+  const size_t np = size_t(nCams) * w * h;
+  const bool changed = nCams != ctx->nCams || w != ctx->width || h != ctx->height;
+  KF_CUDA(ctx, ctx->cams.ensure(nCams));
+  KF_CUDA(ctx, ctx->sum.ensure(np));
+  KF_CUDA(ctx, ctx->rgba.ensure(np));
+  KF_CUDA(ctx, ctx->albedo.ensure(np));
+  KF_CUDA(ctx, ctx->normal.ensure(np));
+  KF_CUDA(ctx, ctx->hitIds.ensure(np));
+  KF_CUDA(ctx, ctx->hitT.ensure(np));
+  KF_CUDA(ctx, ctx->depth.ensure(np));
+  KF_CUDA(ctx, ctx->bgra.ensure(np));
+  if (changed) {
+    KF_CUDA(ctx, cudaMemsetAsync(ctx->rgba.p, 0, sizeof(float4) * np, ctx->stream));
+    KF_CUDA(ctx, cudaMemsetAsync(ctx->bgra.p, 0, sizeof(uchar4) * np, ctx->stream));
+  }
+  ctx->nCams = nCams;
+  ctx->width = w;
+  ctx->height = h;
+  return KFRT_OK;
+}
+
+static SceneDev sceneDev(KfrtContext* ctx) {
+  SceneDev sc{};
+  sc.tlasNodes = ctx->nTlasNodes ? ctx->tlasNodes.p : nullptr;
+  sc.tlasInstIdx = ctx->tlasInstIdx.p;
+  sc.inst = ctx->instRec.p;
+  sc.instSsbo = ctx->instDev.p;
+  sc.geoms = ctx->geomTable.p;
+  sc.mats = ctx->mats.p;
+  sc.texs = ctx->texTable.p;
+  sc.nTex = uint32_t(ctx->texs.size());
+  sc.nInst = uint32_t(ctx->instHost.size());
+  sc.envFaces = ctx->envSize ? ctx->env.p : nullptr;
+  sc.envSize = ctx->envSize;
+  sc.srgbToLinear = ctx->srgbToLinear.p;
+  sc.dl = ctx->dl.p;
+  sc.pl = ctx->pl.p;
+  sc.al = ctx->al.p;
+  return sc;
+}
+
+int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, uint32_t width, uint32_t height,
+               const KfrtPushConstants* pc, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t clockBase) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!cameras || !nCameras || !width || !height || !pc) KF_FAIL(ctx, KFRT_ERR_INVALID, "bad render arguments");
+  if (sampleEnd < sampleBegin || sampleEnd > pc->sampleRatePerPixel)
+    KF_FAIL(ctx, KFRT_ERR_INVALID, "sample range must lie inside [0, sampleRatePerPixel]");
+  if (!ctx->tlasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtRender before kfrtBuildTlas");
+  // material indices are trusted like the reference trusts its SSBO; materials must exist
+  if (ctx->nMats == 0 && !ctx->instHost.empty()) KF_FAIL(ctx, KFRT_ERR_INVALID, "no materials uploaded");
+  if (ctx->texDirty) {
+    int rc = uploadTexTable(ctx);
+    if (rc) return rc;
+  }
+  int rc = ensureOutputs(ctx, nCameras, width, height);
+  if (rc) return rc;
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->cams.p, cameras, sizeof(KfrtCamera) * nCameras, cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * 16, ctx->stream));
+  RenderArgs a;
+  a.sc = sceneDev(ctx);
+  a.cams = ctx->cams.p;
+  a.nCams = nCameras;
+  a.w = width;
+  a.h = height;
+  a.pc = *pc;
+  a.s0 = sampleBegin;
+  a.s1 = sampleEnd;
+  a.clockBase = clockBase;
+  a.sum = ctx->sum.p;
+  a.albedo = ctx->albedo.p;
+  a.normal = ctx->normal.p;
+  a.hitIds = ctx->hitIds.p;
+  a.hitT = ctx->hitT.p;
+  a.depth = ctx->depth.p;
+  a.counters = ctx->counters.p;
+  const dim3 grid((width + 7) / 8, (height + 7) / 8, nCameras);
+  if (ctx->detail)
+    k_render_mega<true><<<grid, 64, 0, ctx->stream>>>(a);
+  else
+    k_render_mega<false><<<grid, 64, 0, ctx->stream>>>(a);
+  KF_CUDA(ctx, cudaGetLastError());
+  ctx->launches = 1;
+  ctx->lastPc = *pc;
+  ctx->rendered = true;
+  ctx->lastCounters = KfrtCounters{};
+  ctx->lastCounters.paths = uint64_t(nCameras) * width * height * (sampleEnd - sampleBegin);
+  return KFRT_OK;
+}
+
+int kfrtResolve(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  if (!ctx->rendered) KF_FAIL(ctx, KFRT_ERR_INVALID, "kfrtResolve before kfrtRender");
+  const size_t np = size_t(ctx->nCams) * ctx->width * ctx->height;
+  k_resolve<<<gridFor(np, 256), 256, 0, ctx->stream>>>(ctx->sum.p, ctx->rgba.p, ctx->bgra.p, np,
+                                                       ctx->lastPc.sampleRatePerPixel, ctx->lastPc.frameCount,
+                                                       ctx->srgbThreshold.p);
+  KF_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return KFRT_OK;
+}
+
+// NCCL is reached the way the reference reaches libcuda (src/cuda_dl.cpp:10-71): dlopen + dlsym,
+// so libkfrt has no link-time dependency on it.
+int kfrtReduceNccl(KfrtContext* ctx, void* ncclComm, int root) {
+  KF_CHECK_CTX(ctx);
+  if (!ctx->rendered || !ncclComm) KF_FAIL(ctx, KFRT_ERR_INVALID, "kfrtReduceNccl needs a rendered frame and a communicator");
+  typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef int (*ReduceFn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+  static void* lib = nullptr;
+  static AllReduceFn allReduce = nullptr;
+  static ReduceFn reduce = nullptr;
+  if (!lib) {
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) KF_FAIL(ctx, KFRT_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    allReduce = reinterpret_cast<AllReduceFn>(dlsym(lib, "ncclAllReduce"));
+    reduce = reinterpret_cast<ReduceFn>(dlsym(lib, "ncclReduce"));
+    if (!allReduce || !reduce) KF_FAIL(ctx, KFRT_ERR_NCCL, "ncclAllReduce/ncclReduce not found");
+  }
+  const size_t count = size_t(ctx->nCams) * ctx->width * ctx->height * 4;
+  const int ncclFloat32 = 7, ncclSum = 0;
+  int r = root < 0 ? allReduce(ctx->sum.p, ctx->sum.p, count, ncclFloat32, ncclSum, ncclComm, ctx->stream)
+                   : reduce(ctx->sum.p, ctx->sum.p, count, ncclFloat32, ncclSum, root, ncclComm, ctx->stream);
+  if (r != 0) KF_FAIL(ctx, KFRT_ERR_NCCL, "NCCL reduce failed with code " + std::to_string(r));
+  return KFRT_OK;
+}
+
+static int bufferOf(KfrtContext* ctx, int kind, void** p, size_t* perPixel) {
+  switch (kind) {
+    case KFRT_AUX_RGBA32F: *p = ctx->rgba.p; *perPixel = 16; return KFRT_OK;
+    case KFRT_AUX_ALBEDO32F: *p = ctx->albedo.p; *perPixel = 16; return KFRT_OK;
+    case KFRT_AUX_NORMAL32F: *p = ctx->normal.p; *perPixel = 16; return KFRT_OK;
+    case KFRT_AUX_HIT_IDS: *p = ctx->hitIds.p; *perPixel = 8; return KFRT_OK;
+    case KFRT_AUX_HIT_T: *p = ctx->hitT.p; *perPixel = 4; return KFRT_OK;
+    case KFRT_AUX_DEPTH: *p = ctx->depth.p; *perPixel = 4; return KFRT_OK;
+    case KFRT_AUX_SUM32F: *p = ctx->sum.p; *perPixel = 16; return KFRT_OK;
+    case KFRT_AUX_BGRA8: *p = ctx->bgra.p; *perPixel = 4; return KFRT_OK;
+    default: return KFRT_ERR_INVALID;
+  }
+}
+
+int kfrtDownloadAux(KfrtContext* ctx, uint32_t camera, int kind, void* dst, size_t nbytes) {
+  KF_CHECK_CTX(ctx);
+  if (!ctx->rendered) KF_FAIL(ctx, KFRT_ERR_INVALID, "nothing rendered yet");
+  if (camera >= ctx->nCams || !dst) KF_FAIL(ctx, KFRT_ERR_INVALID, "bad camera index or destination");
+  const size_t np = size_t(ctx->width) * ctx->height;
+  if (kind == KFRT_AUX_SEGMENTATION) {
+    if (nbytes != np * 4) KF_FAIL(ctx, KFRT_ERR_INVALID, "destination size mismatch");
+    std::vector<int2> ids(np);
+    KF_CUDA(ctx, cudaMemcpyAsync(ids.data(), ctx->hitIds.p + camera * np, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int32_t* o = static_cast<int32_t*>(dst);
+    for (size_t i = 0; i < np; i++) o[i] = ids[i].x;
+    return KFRT_OK;
+  }
+  void* p = nullptr;
+  size_t pp = 0;
+  if (bufferOf(ctx, kind, &p, &pp)) KF_FAIL(ctx, KFRT_ERR_INVALID, "unknown aux kind");
+  if (nbytes != np * pp) KF_FAIL(ctx, KFRT_ERR_INVALID, "destination size mismatch");
+  KF_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<char*>(p) + camera * np * pp, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KFRT_OK;
+}
+
+int kfrtDownloadBGRA8(KfrtContext* ctx, uint32_t camera, uint8_t* dst, size_t nbytes) {
+  return kfrtDownloadAux(ctx, camera, KFRT_AUX_BGRA8, dst, nbytes);
+}
+
+int kfrtGetDeviceBuffer(KfrtContext* ctx, int kind, void** devicePtr, size_t* nbytes) {
+  KF_CHECK_CTX(ctx);
+  if (!devicePtr || !nbytes) KF_FAIL(ctx, KFRT_ERR_INVALID, "null out pointer");
+  void* p = nullptr;
+  size_t pp = 0;
+  if (bufferOf(ctx, kind, &p, &pp)) KF_FAIL(ctx, KFRT_ERR_INVALID, "unknown aux kind");
+  *devicePtr = p;
+  *nbytes = size_t(ctx->nCams) * ctx->width * ctx->height * pp;
+  return KFRT_OK;
+}
+
+int kfrtSetDetailCounters(KfrtContext* ctx, int detail) {
+  KF_CHECK_CTX(ctx);
+  ctx->detail = detail ? 1 : 0;
+  return KFRT_OK;
+}
+
+int kfrtGetCounters(KfrtContext* ctx, KfrtCounters* out) {
+  KF_CHECK_CTX(ctx);
+  if (!out) KF_FAIL(ctx, KFRT_ERR_INVALID, "null counters");
+  unsigned long long h[16] = {0};
+  if (ctx->rendered) {
+    KF_CUDA(ctx, cudaMemcpyAsync(h, ctx->counters.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *out = ctx->lastCounters;
+  out->extensionRays = h[1];
+  out->shadowRays = h[2];
+  out->extensionHits = h[3];
+  out->nodeVisits = h[4];
+  out->triangleTests = h[5];
+  out->instanceVisits = h[6];
+  out->textureFetches = h[7];
+  out->kernelLaunches = ctx->launches;
+  return KFRT_OK;
+}
+
+}  // extern "C"

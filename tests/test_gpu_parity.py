@@ -1,0 +1,145 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded wire buffers.  Bit-exact for hit indices / primitive ids / t / depth at sample 0;
+toleranced for radiance (libm vs CUDA transcendentals; tolerance stated in each test)."""
+import numpy as np
+import pytest
+
+import parity
+import pyscene
+from kuafu_b200 import wire
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    from kuafu_b200 import rt as _rt
+    return _rt
+
+
+@pytest.fixture(scope="module")
+def orc_mod():
+    from oracle import oracle
+    return oracle
+
+
+def _pair(sc, rt, orc_mod):
+    ctx = rt.Context(0)
+    orc = orc_mod.Oracle()
+    sc.upload(ctx)
+    sc.upload(orc)
+    return ctx, orc
+
+
+# Radiance tolerance: per-pixel relative error |gpu-cpu|/(|cpu|+1e-3) may exceed 1e-3 on at most 2 %
+# of pixels (paths whose discrete decisions flip on a 1-ulp sin/cos/pow difference) and the image
+# means must agree to 1e-3 relative.
+def _check_radiance(got, ref, spp):
+    st = parity.radiance_stats(got["sum"], ref["sum"], spp)
+    assert st["frac_gt_1e-3"] < 0.02, st
+    assert st["mean_rel_diff"] < 1e-3, st
+    return st
+
+
+@pytest.mark.parametrize("lights", ["dir", "point", "active", "dir point active"])
+def test_small_scene_hits_and_radiance(rt, orc_mod, lights):
+    sc = pyscene.small_scene(seed=2, w=128, h=96, spp=2, depth=6, lights=lights, textures=True)
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc)
+    parity.assert_hits_bit_exact(got, ref)
+    _check_radiance(got, ref, 2)
+    # ray counts follow the same stochastic decisions; allow the same 2 % slack
+    for k in ("extensionRays", "shadowRays", "extensionHits"):
+        assert abs(got["counters"][k] - ref["counters"][k]) <= 0.02 * max(ref["counters"][k], 1), (k, got["counters"], ref["counters"])
+    assert got["counters"]["paths"] == ref["counters"]["paths"]
+    ctx.close()
+
+
+def test_brute_force_oracle_agrees(rt, orc_mod):
+    """BVH layout must not change the answer: GPU (8-wide LBVH) == oracle brute force over all triangles."""
+    sc = pyscene.small_scene(seed=5, w=64, h=48, spp=1, depth=3, lights="dir", stacks=6, slices=8)
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc, brute=True)
+    parity.assert_hits_bit_exact(got, ref)
+    ctx.close()
+
+
+def test_env_emissive_rr(rt, orc_mod):
+    sc = pyscene.small_scene(seed=3, w=96, h=64, spp=4, depth=8, lights="dir", env=True, emissive=True, rr=True)
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc)
+    parity.assert_hits_bit_exact(got, ref)
+    _check_radiance(got, ref, 4)
+    ctx.close()
+
+
+def test_resolve_and_bgra_bit_exact(rt, orc_mod):
+    """Accumulate + sRGB/BGRA encode of the SAME float sums must be byte-identical."""
+    sc = pyscene.small_scene(seed=4, w=64, h=48, spp=2, depth=4, lights="dir")
+    ctx, orc = _pair(sc, rt, orc_mod)
+    rgba_ref = np.zeros((1, sc.h, sc.w, 4), np.float32)
+    for frame in range(3):
+        sc.pc["frameCount"] = frame
+        ctx.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, clock_base=10 + frame * 3)
+        ctx.resolve()
+        gsum = ctx.download_aux(wire.AUX_SUM32F)[None]
+        bgra_ref = orc.resolve(gsum, rgba_ref, 2, frame)
+        assert np.array_equal(ctx.download_bgra8(), bgra_ref[0])
+        assert np.array_equal(ctx.download_aux(wire.AUX_RGBA32F).view(np.uint32), rgba_ref[0].view(np.uint32))
+    ctx.close()
+
+
+def test_spp_shards_union_equals_full(rt, orc_mod):
+    """spp sharding: samples [0,2) + [2,4) traced separately sum to the 4-spp frame."""
+    sc = pyscene.small_scene(seed=6, w=64, h=48, spp=4, depth=4, lights="dir")
+    ctx, orc = _pair(sc, rt, orc_mod)
+    cams = np.array(sc.cams, wire.CAMERA)
+    ctx.render(cams, sc.w, sc.h, sc.pc, 0, 4, 21)
+    full = ctx.download_aux(wire.AUX_SUM32F).astype(np.float64)
+    ctx.render(cams, sc.w, sc.h, sc.pc, 0, 2, 21)
+    a = ctx.download_aux(wire.AUX_SUM32F).astype(np.float64)
+    ctx.render(cams, sc.w, sc.h, sc.pc, 2, 4, 21)
+    b = ctx.download_aux(wire.AUX_SUM32F).astype(np.float64)
+    assert np.allclose(a[..., :3] + b[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
+    ctx.close()
+
+
+def test_refit_equals_rebuild(rt, orc_mod):
+    """Moving actors: refit of the top level must give the same hits as a fresh build (and the oracle)."""
+    sc = pyscene.small_scene(seed=7, w=96, h=64, spp=1, depth=2, lights="dir")
+    ctx, orc = _pair(sc, rt, orc_mod)
+    insts = np.array(sc.insts, wire.INSTANCE)
+    rng = np.random.default_rng(0)
+    for step in range(3):
+        tr = insts["transform"].copy().reshape(-1, 16)
+        tr[1:, 12:15] += rng.normal(scale=0.7, size=(tr.shape[0] - 1, 3)).astype(np.float32)
+        ctx.refit_tlas(tr)
+        orc.set_transforms(tr)
+        got, ref = parity.render_both(sc, ctx, orc, clock_base=step)
+        parity.assert_hits_bit_exact(got, ref)
+        insts["transform"] = tr
+        ctx2 = rt.Context(0)
+        sc2 = pyscene.small_scene(seed=7, w=96, h=64, spp=1, depth=2, lights="dir")
+        sc2.insts = list(insts)
+        sc2.upload(ctx2)
+        ctx2.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, clock_base=step)
+        assert np.array_equal(ctx2.download_aux(wire.AUX_HIT_IDS), got["hit_ids"][0])
+        ctx2.close()
+    ctx.close()
+
+
+def test_error_behaviour(rt):
+    ctx = rt.Context(0)
+    with pytest.raises(rt.KfrtError) as e:
+        ctx.render(np.zeros(1, wire.CAMERA), 8, 8, wire.push_constants())
+    assert e.value.code == 4  # KFRT_ERR_NOT_BUILT
+    ctx.set_limits(16, 2, 4, 4)
+    v, i = pyscene.quad()
+    ctx.upload_geometry(0, v, i, np.zeros(i.size, np.uint32))
+    with pytest.raises(rt.KfrtError) as e:
+        ctx.upload_geometry(16, v, i, np.zeros(i.size, np.uint32))
+    assert e.value.code == 3  # KFRT_ERR_LIMIT
+    with pytest.raises(rt.KfrtError) as e:
+        ctx.set_instances(np.zeros(3, wire.INSTANCE))
+    assert e.value.code == 3
+    ctx.close()
