@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Kuafu path-tracing core.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): Mrays/s and ms/frame at 1080p, 64 spp on config 3 (the ~1 M-triangle
+instanced PrincipledBSDF scene with textures and an environment cube, path depth 8, Russian roulette
+on).  A "step" is one full frame.  A ray is one traceRayEXT equivalent: every extension ray plus every
+shadow ray actually traced, counted on the device.
+
+N > 1 (one process per GPU under torchrun): the 64 samples of every pixel are split across ranks
+(replicated scene + BVH), the float4 sample sums are reduced onto rank 0 over NCCL and rank 0 runs the
+accumulate + encode epilogue -- strong scaling of one frame.
+
+`value` is timed on the device with everything resident in HBM; `e2e` is the same frame through the
+public facade call (Kuafu::run + downloadLatestFrame) with host buffers, H2D/D2H inside the timed
+region.  `--impl reference` times the CPU oracle (a C++ port of the reference's shaders; the reference's
+Vulkan-RT path cannot run on a B200) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG = {"name": "million", "width": 1920, "height": 1080, "spp": 64, "depth": 8}
+WORKLOAD = ("config 3: 204 x createSphere(4900 tris) + floor = 999602 instanced triangles, 17 textured "
+            "PrincipledBSDF materials (37 512^2 textures), 6x256^2 env cube, directional light, "
+            "1920x1080, 64 spp, path depth 8, Russian roulette on (min 4 bounces)")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    # debugging overrides (a run that uses them is not a bench value; they are echoed in `config`)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--scene", default="")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-spp", type=int, default=1)
+    return ap.parse_args()
+
+
+def effective_config(args):
+    cfg = dict(CONFIG)
+    if args.scene:
+        cfg["name"] = args.scene
+    if args.width:
+        cfg["width"] = args.width
+    if args.height:
+        cfg["height"] = args.height
+    if args.spp:
+        cfg["spp"] = args.spp
+    return cfg
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons while the timed region runs (nvidia-smi, 200 ms)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class DevArray:
+    """__cuda_array_interface__ view of a kfrt device buffer, so torch can run a collective on it."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def algorithmic_bytes(cnt, stats, n_pixels):
+    """SURVEY.md §8.5 accounting: bytes a frame must move given what it visited (layout constants from
+    kfrtGetBvhStats: 80 B wide node, 48 B triangle, 64 B instance record)."""
+    ext, sh, hits = int(cnt["extensionRays"]), int(cnt["shadowRays"]), int(cnt["extensionHits"])
+    rays = ext + sh
+    b = (int(stats["nodeBytes"]) * int(cnt["nodeVisits"]) + int(stats["triangleBytes"]) * int(cnt["triangleTests"]) +
+         int(stats["instanceBytes"]) * int(cnt["instanceVisits"]))
+    b += rays * (32 + 16)
+    b += hits * 240 + 16 * int(cnt["textureFetches"])
+    b += ext * 96
+    b += n_pixels * 36
+    return b, rays
+
+
+def run_reference(args, cfg, rank):
+    """CPU arm: the oracle (C++ port of the reference shaders) on all host cores, bounded sample."""
+    if rank != 0:
+        return
+    from kuafu_b200 import host
+    from oracle import oracle
+    r = host.Renderer(device=None)
+    r.load_scene(cfg["name"], cfg["width"], cfg["height"], cfg["spp"], cfg["depth"])
+    ws = r.wire_scene()
+    orc = oracle.Oracle()
+    ws.upload(orc)
+    cores = oracle.hardware_threads()
+    sample_spp = max(1, min(args.cpu_sample_spp, cfg["spp"]))
+    cams = np.array(ws.cams[:1])
+
+    def step(i):
+        t = time.perf_counter()
+        out = orc.render(cams, ws.w, ws.h, ws.pc, 0, sample_spp, clock_base=i * (cfg["spp"] + 1), threads=cores)
+        dt = time.perf_counter() - t
+        c = out["counters"]
+        return dt, c["extensionRays"] + c["shadowRays"]
+
+    for i in range(args.warmup):
+        step(i)
+    tot_t, tot_r = 0.0, 0
+    for i in range(args.steps):
+        dt, rays = step(args.warmup + i)
+        tot_t += dt
+        tot_r += rays
+    mrays = tot_r / tot_t / 1e6
+    scale = cfg["spp"] / sample_spp
+    sample = (f"{sample_spp} of {cfg['spp']} spp of every pixel per step ({cfg['width']}x{cfg['height']}); "
+              f"ms_per_step is the sample time x {scale:g}")
+    line = {
+        "impl": "reference", "metric": "Mrays/s (path tracing, 1080p 64 spp, config 3)", "value": mrays,
+        "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_t / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, **cfg},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    cfg = effective_config(args)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kuafu_b200 import host, rt, wire
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    spp = cfg["spp"]
+    s0, s1 = rank * spp // world, (rank + 1) * spp // world
+
+    # ---- scene through the facade (public API), device context borrowed for the resident-timed arm
+    renderer = host.Renderer(device=local_rank, accumulate=False)
+    renderer.load_scene(cfg["name"], cfg["width"], cfg["height"], spp, cfg["depth"])
+    ws = renderer.wire_scene()
+    if world > 1:
+        renderer.set_sample_shard(s0, s1, defer_resolve=True)
+    stream = torch.cuda.current_stream()
+    ctx = rt.Context(handle=renderer.device_context())
+    ctx.set_stream(stream.cuda_stream)
+    renderer.run()  # uploads, builds BLAS/TLAS, renders once
+    torch.cuda.synchronize()
+    stats = ctx.bvh_stats()
+    cams = np.array(ws.cams[:1], wire.CAMERA)
+    pc = ws.pc
+    n_pixels = cfg["width"] * cfg["height"]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    sum_ptr, sum_bytes = ctx.device_buffer(wire.AUX_SUM32F)
+    sum_t = torch.as_tensor(DevArray(sum_ptr, sum_bytes), device="cuda") if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame(i, ev=None):
+        """One resident step: trace this rank's samples, reduce, accumulate + encode."""
+        if ev:
+            ev[0].record(stream)
+        ctx.render(cams, cfg["width"], cfg["height"], pc, s0, s1, clock_base=i * (spp + 1))
+        if ev:
+            ev[1].record(stream)
+        if world > 1:
+            dist.reduce(sum_t, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            ctx.resolve()
+        if ev:
+            ev[2].record(stream)
+
+    for i in range(args.warmup):
+        frame(i)
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    rays_total, launches = 0, 0
+    counters = []
+    for k in range(args.steps):
+        frame(args.warmup + k, events[k])
+        c = ctx.counters()  # synchronises; outside the event brackets
+        counters.append(c)
+        launches += int(c["kernelLaunches"]) if rank == 0 else 1
+        flush.zero_()  # L2 flush between timed steps
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [events[k][0].elapsed_time(events[k][2]) for k in range(args.steps)]
+    render_ms = [events[k][0].elapsed_time(events[k][1]) for k in range(args.steps)]
+    my_rays = sum(int(c["extensionRays"]) + int(c["shadowRays"]) for c in counters)
+    tot = torch.tensor([sum(step_ms), float(my_rays), sum(render_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, rays_total, render_total_ms = float(mx[0]), float(sm[1]), float(mx[2])
+    else:
+        total_ms, rays_total, render_total_ms = float(tot[0]), float(tot[1]), float(tot[2])
+    value = rays_total / (total_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (the trace kernel), rank 0: counts from one untimed
+    # detail-counter pass with the seeds of the last timed step, duration from the timed steps
+    roof = None
+    if rank == 0:
+        ctx.set_detail_counters(True)
+        ctx.render(cams, cfg["width"], cfg["height"], pc, s0, s1, clock_base=(args.warmup + args.steps - 1) * (spp + 1))
+        detail = ctx.counters()
+        ctx.set_detail_counters(False)
+        abytes, rays = algorithmic_bytes(detail, stats, n_pixels)
+        peak, peak_src = measured_peaks()
+        dur = statistics.mean(render_ms) * 1e-3
+        achieved = abytes / dur / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "trace (ray generation + traversal + shading)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
+                "bytes_per_ray": abytes / max(rays, 1),
+                "per_ray": {"nodes": int(detail["nodeVisits"]) / max(rays, 1),
+                            "triangles": int(detail["triangleTests"]) / max(rays, 1),
+                            "instances": int(detail["instanceVisits"]) / max(rays, 1)},
+                "kernel_ms": statistics.mean(render_ms)}
+
+    # ---- e2e: the user-facing call (Kuafu::run + downloadLatestFrame) with host buffers
+    e2e_t, e2e_rays = 0.0, 0
+    h2d = 320 + 48 + 2592 + 64 * int(stats["instanceCount"])  # camera, push constants, lights, transforms
+    d2h = n_pixels * 4
+    for i in range(2):
+        renderer.clock_base = (1000 + i) * (spp + 1)
+        renderer.run()
+    barrier()
+    for k in range(args.steps):
+        renderer.clock_base = (2000 + k) * (spp + 1)
+        barrier()
+        t = time.perf_counter()
+        renderer.run()
+        if world > 1:
+            dist.reduce(sum_t, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            if world > 1:
+                renderer.resolve()
+            frame_bytes = renderer.download_frame(0)
+            assert frame_bytes.nbytes == d2h
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        c = ctx.counters()
+        r = torch.tensor([dt, float(int(c["extensionRays"]) + int(c["shadowRays"]))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            m = r.clone()
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            s = r.clone()
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            e2e_t += float(m[0])
+            e2e_rays += float(s[1])
+        else:
+            e2e_t += dt
+            e2e_rays += float(r[1])
+    e2e_value = e2e_rays / e2e_t / 1e6
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        orc = oracle.Oracle()
+        ws.upload(orc)
+        cores = oracle.hardware_threads()
+        sample_spp = max(1, min(args.cpu_sample_spp, spp))
+        t = time.perf_counter()
+        out = orc.render(cams, ws.w, ws.h, pc, 0, sample_spp, clock_base=0, threads=cores)
+        dt = time.perf_counter() - t
+        cr = out["counters"]["extensionRays"] + out["counters"]["shadowRays"]
+        cpu = {"value": cr / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+               "sample": f"{sample_spp} of {spp} spp of every pixel ({ws.w}x{ws.h}), one pass, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s (path tracing, 1080p 64 spp, config 3)", "value": value, "unit": "Mrays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, **cfg, "parallelism": f"spp-shard x{world}",
+                       "l2": "flushed between timed steps (512 MiB memset)",
+                       "triangles_instanced": int(stats["instancedTriangles"]),
+                       "instances": int(stats["instanceCount"])},
+            "per_gpu_mrays": value / world,
+            "rays_per_step": rays_total / args.steps,
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_t / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,3 +1,3 @@
 set -x
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-python -m pytest tests -m gpu -x -q 2>&1 | tail -40
+python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+python bench.py --steps 2 --warmup 1 --spp 8 2>&1 | tail -5

@@ -1,0 +1,16 @@
+// Texture / cube-map file decoding for the host facade (stands in for the reference's stb_image +
+// libktx use in vkCore.hpp:1761-1795,1853-1971).  Everything is expanded to RGBA8 like
+// stbi_load(..., STBI_rgb_alpha).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace kuafu::io {
+/// "mem:<name>" (global::registerMemoryTexture), .png (8-bit, non-interlaced), .ppm/.pgm (P6/P5).
+bool loadTextureRGBA8(const std::string& path, uint32_t& width, uint32_t& height, std::vector<uint8_t>& rgba);
+/// KTX1, uncompressed RGBA8 / SRGB8_ALPHA8, six faces, level 0.
+bool loadKtxCubeRGBA8(const std::string& path, uint32_t& size, std::vector<uint8_t> faces[6]);
+bool decodePng(const uint8_t* data, size_t n, uint32_t& width, uint32_t& height, std::vector<uint8_t>& rgba);
+bool writePpm(const std::string& path, uint32_t width, uint32_t height, const uint8_t* rgb);
+}  // namespace kuafu::io

@@ -76,8 +76,13 @@ _AUX = {
 class Context:
     """One KfrtContext.  Method names follow the C entry points."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.lib = load()
+        self.owned = handle is None
+        self.shape = None
+        if handle is not None:  # borrow the KfrtContext that lives under a facade renderer
+            self.h = C.c_void_p(handle)
+            return
         h = C.c_void_p()
         rc = self.lib.kfrtCreate(int(device), C.byref(h))
         if rc:
@@ -90,9 +95,9 @@ class Context:
             raise KfrtError(rc, self.lib.kfrtLastError(self.h).decode())
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.lib.kfrtDestroy(self.h)
-            self.h = None
+        self.h = None
 
     def __enter__(self):
         return self
@@ -173,7 +178,7 @@ class Context:
         cams = _arr(cameras, wire.CAMERA).reshape(-1)
         pc = _arr(pc, wire.PUSH_CONSTANTS)
         if sample_end is None:
-            sample_end = int(pc["sampleRatePerPixel"])
+            sample_end = int(pc.reshape(-1)[0]["sampleRatePerPixel"])
         self._ck(self.lib.kfrtRender(self.h, _ptr(cams), cams.size, width, height, _ptr(pc), sample_begin,
                                      sample_end, clock_base & 0xFFFFFFFF))
         self.shape = (cams.size, height, width)

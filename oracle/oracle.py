@@ -136,7 +136,7 @@ class Oracle:
         pc = np.ascontiguousarray(pc)
         assert pc.dtype.itemsize == 48
         if sample_end is None:
-            sample_end = int(pc["sampleRatePerPixel"])
+            sample_end = int(pc.reshape(-1)[0]["sampleRatePerPixel"])
         n = cams.size
         out = {
             "sum": np.zeros((n, height, width, 4), "<f4"),
