@@ -228,7 +228,9 @@ def main():
     ws = renderer.wire_scene()
     if world > 1:
         renderer.set_sample_shard(s0, s1, defer_resolve=True)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: kfrt launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = rt.Context(handle=renderer.device_context())
     ctx.set_stream(stream.cuda_stream)
     renderer.run()  # uploads, builds BLAS/TLAS, renders once

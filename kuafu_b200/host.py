@@ -75,6 +75,8 @@ class WireSceneView:
 
     def upload(self, target):
         is_rt = hasattr(target, "upload_geometry")
+        if is_rt:  # Config limits of the facade renderer that packed this scene (kfcCreate)
+            target.set_limits(1025, 8192, 257, 4097)
         for gi, (v, idx, mi, op, hide) in enumerate(self.geoms):
             (target.upload_geometry if is_rt else target.set_geometry)(gi, v, idx, mi, op, hide)
         (target.upload_materials if is_rt else target.set_materials)(self.mats)
