@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "kf_common.cuh"
 #include "kf_shade.cuh"
 #include "kf_traverse.cuh"
+#include "kf_wavefront.cuh"
 
 using namespace kf;
 
@@ -143,6 +145,16 @@ struct KfrtContext {
   bool rendered = false;
   int detail = 0;
   uint64_t launches = 0;
+  // wavefront scheduler state
+  int numSMs = 148;
+  int scheduler = 1;  // 1 wavefront (default), 0 megakernel (KFRT_SCHEDULER=mega; round-1 baseline kept for A/B)
+  size_t batchSlotTarget = size_t(16) << 20;
+  size_t wfSlots = 0;
+  bool wfMulti = false;
+  DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
+  DevBuf<int> wfHitB;
+  DevBuf<uint32_t> wfQueue0, wfQueue1, wfShadowQ0, wfShadowQ1, wfCounts;
+  int gridExtend[2] = {0, 0}, gridShade[4] = {0, 0, 0, 0}, gridShadow[4] = {0, 0, 0, 0}, gridRaygen = 0;
   KfrtCounters lastCounters{};
 };
 
@@ -358,38 +370,6 @@ KF_D unsigned long long warpSum(unsigned long long v) {
   return v;
 }
 
-// Camera ray of one sample (reference PathTrace.rgen:35-56), contract arithmetic: the primary-ray
-// bits must equal the oracle's so that 1-spp hit buffers can be compared bit-exactly.
-KF_D void cameraRay(const KfrtCamera* __restrict__ cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
-                    uint32_t& pixelSeed, uint32_t& raySeed, V3& o, V3& d) {
-  const float jx = rnd(pixelSeed);
-  const float jy = rnd(pixelSeed);
-  const float px = cadd(float(x), jx), py = cadd(float(y), jy);
-  const float nx = cdiv(px, float(w)), ny = cdiv(py, float(h));
-  const float dx = csub(cmul(nx, 2.0f), 1.0f), dy = csub(cmul(ny, 2.0f), 1.0f);
-  const float aperture = cam->position[3];
-  const float focus = cam->front[3];
-  float ox, oy;
-  diskSampling(raySeed, ox, oy);
-  ox = cmul(cdiv(aperture, 2.0f), ox);
-  oy = cmul(cdiv(aperture, 2.0f), oy);
-  float target[4], origin[4], direction[4];
-  cmulMat4(cam->projectionInverse, dx, dy, 1.0f, 1.0f, target);
-  if (aperture > 0.0f) {
-    cmulMat4(cam->viewInverse, ox, oy, 0.0f, 1.0f, origin);
-    const V3 t = mk3(csub(cmul(target[0], focus), ox), csub(cmul(target[1], focus), oy),
-                     csub(cmul(target[2], focus), 0.0f));
-    const V3 dd = cnormalize(t);
-    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
-  } else {
-    cmulMat4(cam->viewInverse, 0.0f, 0.0f, 0.0f, 1.0f, origin);
-    const V3 dd = cnormalize(mk3(target[0], target[1], target[2]));
-    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
-  }
-  o = mk3(origin[0], origin[1], origin[2]);
-  d = mk3(direction[0], direction[1], direction[2]);
-}
-
 // One thread per pixel: the whole of PathTrace.rgen:19-141 with traversal and shading inlined.
 // (Round-1 baseline scheduler; the wavefront scheduler reuses the same device functions.)
 template <bool DETAIL>
@@ -591,6 +571,12 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
     return KFRT_ERR_CUDA;
   }
   ctx->stream = ctx->ownStream;
+  ctx->numSMs = prop.multiProcessorCount;
+  if (const char* e = std::getenv("KFRT_SCHEDULER")) ctx->scheduler = std::strcmp(e, "mega") == 0 ? 0 : 1;
+  if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
+    const long long v = std::atoll(e);
+    if (v > 0) ctx->batchSlotTarget = size_t(v);
+  }
   // sRGB decode table and encode thresholds (same double-precision formulas as the oracle)
   float lut[256], thr[255];
   for (int i = 0; i < 256; i++) {
@@ -633,6 +619,10 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
   ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
   ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
+  ctx->wfRayO.release(); ctx->wfRayD.release(); ctx->wfHitA.release(); ctx->wfStateW.release();
+  ctx->wfStateC.release(); ctx->wfShadowL.release(); ctx->wfShadowC.release(); ctx->wfCtx.release();
+  ctx->wfHitB.release(); ctx->wfQueue0.release(); ctx->wfQueue1.release(); ctx->wfShadowQ0.release();
+  ctx->wfShadowQ1.release(); ctx->wfCounts.release();
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
   delete ctx;
   return KFRT_OK;
@@ -906,6 +896,140 @@ int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   return KFRT_OK;
 }
 
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Wavefront scheduler (host side): sizes the path-state buffers, then sequences the stage kernels.
+// No host synchronisation inside a frame: queue sizes stay on the device and every stage runs as a
+// persistent grid (a multiple of the SM count) that strides over its queue.
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static int persistentGrid(KfrtContext* ctx, K kernel, int blockSize) {
+  int perSm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, blockSize, 0) != cudaSuccess || perSm < 1) perSm = 1;
+  return ctx->numSMs * perSm;
+}
+
+static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
+  const uint32_t tilesX = (ra.w + 7) / 8, tilesY = (ra.h + 3) / 4;
+  const size_t slotsPerSample = size_t(ra.nCams) * tilesX * tilesY * 32;
+  const uint32_t nSamples = ra.s1 - ra.s0;
+  ctx->launches = 0;
+  if (nSamples == 0) {
+    KF_CUDA(ctx, cudaMemsetAsync(ra.sum, 0, sizeof(float4) * size_t(ra.nCams) * ra.w * ra.h, ctx->stream));
+    return KFRT_OK;
+  }
+  uint32_t batch = uint32_t(std::max<size_t>(1, ctx->batchSlotTarget / slotsPerSample));
+  batch = std::min(batch, nSamples);
+  const size_t slots = slotsPerSample * batch;
+  if (slots >= (size_t(1) << 31)) KF_FAIL(ctx, KFRT_ERR_INVALID, "too many pixels for one batch");
+  const bool multi = ctx->nLightSlots > 1;
+  KF_CUDA(ctx, ctx->wfRayO.ensure(slots));
+  KF_CUDA(ctx, ctx->wfRayD.ensure(slots));
+  KF_CUDA(ctx, ctx->wfHitA.ensure(slots));
+  KF_CUDA(ctx, ctx->wfHitB.ensure(slots));
+  KF_CUDA(ctx, ctx->wfStateW.ensure(slots));
+  KF_CUDA(ctx, ctx->wfStateC.ensure(slots));
+  KF_CUDA(ctx, ctx->wfShadowL.ensure(slots));
+  KF_CUDA(ctx, ctx->wfShadowC.ensure(slots));
+  if (multi) KF_CUDA(ctx, ctx->wfCtx.ensure(slots * 6));
+  KF_CUDA(ctx, ctx->wfQueue0.ensure(slots));
+  KF_CUDA(ctx, ctx->wfQueue1.ensure(slots));
+  KF_CUDA(ctx, ctx->wfShadowQ0.ensure(slots));
+  if (multi) KF_CUDA(ctx, ctx->wfShadowQ1.ensure(slots));
+  KF_CUDA(ctx, ctx->wfCounts.ensure(4));
+  if (!ctx->gridRaygen) {
+    ctx->gridRaygen = persistentGrid(ctx, k_wf_raygen, 256);
+    ctx->gridExtend[0] = persistentGrid(ctx, k_wf_extend<false>, 128);
+    ctx->gridExtend[1] = persistentGrid(ctx, k_wf_extend<true>, 128);
+    ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, 128);
+    ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, 128);
+    ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, 128);
+    ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true>, 128);
+    ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow<false, false>, 128);
+    ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow<false, true>, 128);
+    ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow<true, false>, 128);
+    ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow<true, true>, 128);
+  }
+  WfArgs a;
+  a.sc = ra.sc;
+  a.b.rayO = ctx->wfRayO.p;
+  a.b.rayD = ctx->wfRayD.p;
+  a.b.hitA = ctx->wfHitA.p;
+  a.b.hitB = ctx->wfHitB.p;
+  a.b.stateW = ctx->wfStateW.p;
+  a.b.stateC = ctx->wfStateC.p;
+  a.b.shadowL = ctx->wfShadowL.p;
+  a.b.shadowC = ctx->wfShadowC.p;
+  a.b.ctx = ctx->wfCtx.p;
+  a.b.queue[0] = ctx->wfQueue0.p;
+  a.b.queue[1] = ctx->wfQueue1.p;
+  a.b.shadowQueue[0] = ctx->wfShadowQ0.p;
+  a.b.shadowQueue[1] = multi ? ctx->wfShadowQ1.p : ctx->wfShadowQ0.p;
+  a.b.counts = ctx->wfCounts.p;
+  a.cams = ra.cams;
+  a.nCams = ra.nCams;
+  a.w = ra.w;
+  a.h = ra.h;
+  a.tilesX = tilesX;
+  a.tilesY = tilesY;
+  a.slotsPerSample = uint32_t(slotsPerSample);
+  a.firstSample = ra.s0;
+  a.pc = ra.pc;
+  a.clockBase = ra.clockBase;
+  a.sum = ra.sum;
+  a.albedo = ra.albedo;
+  a.normal = ra.normal;
+  a.hitIds = ra.hitIds;
+  a.hitT = ra.hitT;
+  a.depth = ra.depth;
+  a.counters = ra.counters;
+  const int d = ctx->detail ? 1 : 0;
+  const int variant = (multi ? 2 : 0) + d;
+  cudaStream_t st = ctx->stream;
+  for (uint32_t b0 = ra.s0; b0 < ra.s1; b0 += batch) {
+    a.batchBegin = b0;
+    a.batchCount = std::min(batch, ra.s1 - b0);
+    KF_CUDA(ctx, cudaMemsetAsync(a.b.counts, 0, 4 * sizeof(uint32_t), st));
+    k_wf_raygen<<<ctx->gridRaygen, 256, 0, st>>>(a);
+    ctx->launches++;
+    for (uint32_t depth = 0; depth <= ra.pc.maxPathDepth; depth++) {
+      const int q = int(depth & 1u);
+      if (d) k_wf_extend<true><<<ctx->gridExtend[1], 128, 0, st>>>(a, q);
+      else k_wf_extend<false><<<ctx->gridExtend[0], 128, 0, st>>>(a, q);
+      switch (variant) {
+        case 0: k_wf_shade<false, false><<<ctx->gridShade[0], 128, 0, st>>>(a, q, depth); break;
+        case 1: k_wf_shade<false, true><<<ctx->gridShade[1], 128, 0, st>>>(a, q, depth); break;
+        case 2: k_wf_shade<true, false><<<ctx->gridShade[2], 128, 0, st>>>(a, q, depth); break;
+        default: k_wf_shade<true, true><<<ctx->gridShade[3], 128, 0, st>>>(a, q, depth); break;
+      }
+      ctx->launches += 2;
+      const uint32_t rounds = ctx->nLightSlots;
+      for (uint32_t l = 0; l < rounds; l++) {
+        const int sq = multi ? int(l & 1u) : 0;
+        switch (variant) {
+          case 0: k_wf_shadow<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          case 1: k_wf_shadow<false, true><<<ctx->gridShadow[1], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          case 2: k_wf_shadow<true, false><<<ctx->gridShadow[2], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          default: k_wf_shadow<true, true><<<ctx->gridShadow[3], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+        }
+        ctx->launches++;
+        if (multi && l + 1 < rounds) {
+          k_wf_clear_count<<<1, 1, 0, st>>>(a.b.counts + 2 + sq);
+          ctx->launches++;
+        }
+      }
+    }
+    k_wf_finish<<<gridFor(slotsPerSample, 256), 256, 0, st>>>(a);
+    ctx->launches++;
+  }
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+extern "C" {
+
 static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t h) {
   const size_t np = size_t(nCams) * w * h;
   const bool changed = nCams != ctx->nCams || w != ctx->width || h != ctx->height;
@@ -983,13 +1107,18 @@ int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, u
   a.hitT = ctx->hitT.p;
   a.depth = ctx->depth.p;
   a.counters = ctx->counters.p;
-  const dim3 grid((width + 7) / 8, (height + 7) / 8, nCameras);
-  if (ctx->detail)
-    k_render_mega<true><<<grid, 64, 0, ctx->stream>>>(a);
-  else
-    k_render_mega<false><<<grid, 64, 0, ctx->stream>>>(a);
-  KF_CUDA(ctx, cudaGetLastError());
-  ctx->launches = 1;
+  if (ctx->scheduler == 0) {
+    const dim3 grid((width + 7) / 8, (height + 7) / 8, nCameras);
+    if (ctx->detail)
+      k_render_mega<true><<<grid, 64, 0, ctx->stream>>>(a);
+    else
+      k_render_mega<false><<<grid, 64, 0, ctx->stream>>>(a);
+    KF_CUDA(ctx, cudaGetLastError());
+    ctx->launches = 1;
+  } else {
+    rc = renderWavefront(ctx, a);
+    if (rc) return rc;
+  }
   ctx->lastPc = *pc;
   ctx->rendered = true;
   ctx->lastCounters = KfrtCounters{};

@@ -434,4 +434,36 @@ KF_D bool nextLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& 
   return false;
 }
 
+// Camera ray of one sample (reference PathTrace.rgen:35-56), contract arithmetic: the primary-ray
+// bits must equal the oracle's so that 1-spp hit buffers can be compared bit-exactly.
+KF_D void cameraRay(const KfrtCamera* __restrict__ cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
+                    uint32_t& pixelSeed, uint32_t& raySeed, V3& o, V3& d) {
+  const float jx = rnd(pixelSeed);
+  const float jy = rnd(pixelSeed);
+  const float px = cadd(float(x), jx), py = cadd(float(y), jy);
+  const float nx = cdiv(px, float(w)), ny = cdiv(py, float(h));
+  const float dx = csub(cmul(nx, 2.0f), 1.0f), dy = csub(cmul(ny, 2.0f), 1.0f);
+  const float aperture = cam->position[3];
+  const float focus = cam->front[3];
+  float ox, oy;
+  diskSampling(raySeed, ox, oy);
+  ox = cmul(cdiv(aperture, 2.0f), ox);
+  oy = cmul(cdiv(aperture, 2.0f), oy);
+  float target[4], origin[4], direction[4];
+  cmulMat4(cam->projectionInverse, dx, dy, 1.0f, 1.0f, target);
+  if (aperture > 0.0f) {
+    cmulMat4(cam->viewInverse, ox, oy, 0.0f, 1.0f, origin);
+    const V3 t = mk3(csub(cmul(target[0], focus), ox), csub(cmul(target[1], focus), oy),
+                     csub(cmul(target[2], focus), 0.0f));
+    const V3 dd = cnormalize(t);
+    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
+  } else {
+    cmulMat4(cam->viewInverse, 0.0f, 0.0f, 0.0f, 1.0f, origin);
+    const V3 dd = cnormalize(mk3(target[0], target[1], target[2]));
+    cmulMat4(cam->viewInverse, dd.x, dd.y, dd.z, 0.0f, direction);
+  }
+  o = mk3(origin[0], origin[1], origin[2]);
+  d = mk3(direction[0], direction[1], direction[2]);
+}
+
 }  // namespace kf

@@ -1,0 +1,394 @@
+// kf_wavefront.cuh -- wavefront path tracing: the reference's raygen -> closest-hit -> shadow
+// recursion (PathTrace.rgen:30-141, PathTrace.rchit:322-469) unrolled into per-stage kernels over
+// compacted queues, so that every warp runs one stage with (almost) all lanes alive.
+//
+// Per batch of S samples of every pixel (slot = sample * nPixelSlots + tiled pixel index):
+//
+//   k_wf_raygen            camera ray + RNG seeds, path state, queue 0
+//   for depth = 0 .. maxPathDepth:
+//     k_wf_extend          closest hit of every queued ray            (traverse<false>)
+//     k_wf_shade           miss / emissive -> path ends; surface -> BSDF sample, first light that
+//                          needs an occlusion ray (speculative contribution), or advance directly
+//     k_wf_shadow (x L)    occlusion ray (traverse<true>), resolve the light, walk to the next light
+//                          (multi-light scenes), then advance: Russian roulette, enqueue next bounce
+//   k_wf_finish            per pixel: add the S sample colours in sample order onto the sum buffer
+//
+// The per-path LCG stream is consumed in exactly the reference order: lobe choice, lobe sample,
+// per light [perturbation, (if unoccluded) calcDirectContribution draw], Russian roulette.  The
+// contribution of the light whose occlusion ray is in flight is evaluated speculatively on a copy of
+// the seed; the shadow kernel commits (contribution, advanced seed) only when the ray is unoccluded.
+#pragma once
+
+#include "kf_common.cuh"
+#include "kf_shade.cuh"
+#include "kf_traverse.cuh"
+
+namespace kf {
+
+// Surface context spilled between light iterations (multi-light scenes only), 6 x float4.
+struct WfBuffers {
+  float4* rayO;     // origin.xyz, -
+  float4* rayD;     // direction.xyz, -
+  float4* hitA;     // t, u, v, prim (bits)
+  int* hitB;        // inst | front << 31, -1 on miss
+  float4* stateW;   // throughput weight.xyz, seed (bits)
+  float4* stateC;   // colour.xyz, -
+  float4* shadowL;  // L.xyz, maxDist
+  float4* shadowC;  // speculative contribution.xyz, seed after calcDirect (bits)
+  float4* ctx;      // 6 per slot (multi-light): N|f, V|a2, diffuse|isInside, specular|k, transmission|-, shadowAcc|-
+  uint32_t* queue[2];
+  uint32_t* shadowQueue[2];
+  uint32_t* counts;  // [0..1] extension queue sizes, [2..3] shadow queue sizes
+};
+
+struct WfArgs {
+  SceneDev sc;
+  WfBuffers b;
+  const KfrtCamera* cams;
+  uint32_t nCams, w, h, tilesX, tilesY;  // 8 x 4 pixel tiles
+  uint32_t slotsPerSample;               // nCams * tilesX * tilesY * 32
+  uint32_t batchBegin, batchCount;       // global sample index of the first sample, samples in batch
+  uint32_t firstSample;                  // sampleBegin of the kfrtRender call
+  KfrtPushConstants pc;
+  uint32_t clockBase;
+  float4* sum;
+  float4* albedo;
+  float4* normal;
+  int2* hitIds;
+  float* hitT;
+  float* depth;
+  unsigned long long* counters;
+};
+
+KF_D void slotToPixel(const WfArgs& a, uint32_t pixelSlot, uint32_t& cam, uint32_t& x, uint32_t& y) {
+  const uint32_t lane = pixelSlot & 31u;
+  uint32_t tile = pixelSlot >> 5;
+  const uint32_t tilesPerCam = a.tilesX * a.tilesY;
+  cam = tile / tilesPerCam;
+  tile -= cam * tilesPerCam;
+  const uint32_t ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
+  x = tx * 8 + (lane & 7u);
+  y = ty * 4 + (lane >> 3);
+}
+
+// Warp-aggregated append: one atomic per warp, lanes get consecutive positions.
+KF_D void queueAppend(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, bool pred, uint32_t value) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+KF_D void countAdd(unsigned long long* c, bool pred) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if ((threadIdx.x & 31) == 0 && mask) atomicAdd(c, (unsigned long long)__popc(mask));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
+  const uint32_t total = a.slotsPerSample * a.batchCount;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.b.counts[1] = 0;
+    a.b.counts[2] = 0;
+    a.b.counts[3] = 0;
+  }
+  for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+    const uint32_t slot = base + threadIdx.x;
+    bool valid = slot < total;
+    uint32_t cam = 0, x = 0, y = 0, s = 0;
+    if (valid) {
+      s = slot / a.slotsPerSample;
+      slotToPixel(a, slot - s * a.slotsPerSample, cam, x, y);
+      valid = x < a.w && y < a.h;
+    }
+    if (valid) {
+      const uint32_t i = a.batchBegin + s;  // global sample index
+      const uint32_t mapping = y * a.w + x;
+      uint32_t seed = tea(mapping, a.clockBase);
+      // the pixel-jitter stream is shared by all samples of the pixel: skip the draws of samples < i
+      for (uint32_t k = 0; k < 2 * i; k++) lcg(seed);
+      uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
+      V3 o, d;
+      cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);
+      a.b.rayO[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+      a.b.rayD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+      a.b.stateW[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(raySeed));
+      a.b.stateC[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    queueAppend(a.b.queue[0], a.b.counts + 0, valid, slot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool DETAIL>
+__global__ void __launch_bounds__(128) k_wf_extend(WfArgs a, int q) {
+  const uint32_t count = a.b.counts[q];
+  const uint32_t* __restrict__ queue = a.b.queue[q];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.b.counts[q ^ 1] = 0;  // next extension queue and both shadow queues are empty during this stage
+    a.b.counts[2] = 0;
+    a.b.counts[3] = 0;
+    atomicAdd(a.counters + 1, (unsigned long long)count);
+  }
+  TravCounters tc{0, 0, 0};
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint32_t slot = queue[i];
+    const float4 o = a.b.rayO[slot], d = a.b.rayD[slot];
+    const uint32_t seed = __float_as_uint(a.b.stateW[slot].w);
+    Hit hit;
+    traverse<false, DETAIL>(a.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.001f, 10000.0f, seed, hit, tc);
+    a.b.hitA[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.prim));
+    a.b.hitB[slot] = hit.inst < 0 ? -1 : int(uint32_t(hit.inst) | (hit.front << 31));
+  }
+  if (DETAIL) {
+    atomicAdd(a.counters + 4, (unsigned long long)tc.nodes);
+    atomicAdd(a.counters + 5, (unsigned long long)tc.tris);
+    atomicAdd(a.counters + 6, (unsigned long long)tc.insts);
+  }
+}
+
+// Russian roulette and hand-over to the next bounce (reference PathTrace.rgen:119-138).
+// Returns true when the path continues.
+KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, uint32_t& seed) {
+  if (allEq(weight, mk3(0.0f))) return false;
+  if (pc.russianRoulette && depth >= pc.russianRouletteMinBounces) {
+    const float p = fmaxf(weight.x, fmaxf(weight.y, weight.z));
+    const float r = rnd(seed);
+    if (r > p) return false;
+    weight *= 1.0f / p;
+  }
+  return depth < pc.maxPathDepth;
+}
+
+KF_D void storeCtx(float4* __restrict__ c, const Surface& sf, int k, V3 acc) {
+  c[0] = make_float4(sf.N.x, sf.N.y, sf.N.z, sf.f);
+  c[1] = make_float4(sf.V.x, sf.V.y, sf.V.z, sf.a2);
+  c[2] = make_float4(sf.diffuseColor.x, sf.diffuseColor.y, sf.diffuseColor.z, __uint_as_float(sf.isInside));
+  c[3] = make_float4(sf.specularColor.x, sf.specularColor.y, sf.specularColor.z, __int_as_float(k));
+  c[4] = make_float4(sf.transmissionColor.x, sf.transmissionColor.y, sf.transmissionColor.z, 0.0f);
+  c[5] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+}
+KF_D void loadCtx(const float4* __restrict__ c, Surface& sf, int& k, V3& acc) {
+  const float4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
+  sf.N = mk3(c0.x, c0.y, c0.z);
+  sf.f = c0.w;
+  sf.V = mk3(c1.x, c1.y, c1.z);
+  sf.a2 = c1.w;
+  sf.diffuseColor = mk3(c2.x, c2.y, c2.z);
+  sf.isInside = __float_as_uint(c2.w);
+  sf.specularColor = mk3(c3.x, c3.y, c3.z);
+  k = __float_as_int(c3.w);
+  sf.transmissionColor = mk3(c4.x, c4.y, c4.z);
+  acc = mk3(c5.x, c5.y, c5.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool MULTI, bool DETAIL>
+__global__ void __launch_bounds__(128) k_wf_shade(WfArgs a, int q, uint32_t depth) {
+  const uint32_t count = a.b.counts[q];
+  const uint32_t* __restrict__ queue = a.b.queue[q];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  unsigned long long texTotal = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < count;
+    bool toNext = false, toShadow = false, isHit = false;
+    uint32_t slot = 0;
+    if (valid) {
+      slot = queue[i];
+      const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[slot];
+      const int hB = a.b.hitB[slot];
+      const float4 sw = a.b.stateW[slot];
+      float4 sc4 = a.b.stateC[slot];
+      V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
+      uint32_t seed = __float_as_uint(sw.w);
+      const V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
+      uint32_t tex = 0;
+      const uint32_t s = slot / a.slotsPerSample;
+      const bool firstHitOutputs = depth == 0 && (a.batchBegin + s) == 0;  // sample 0, depth 0
+      uint32_t cam = 0, px = 0, py = 0;
+      size_t pi = 0;
+      if (firstHitOutputs) {
+        slotToPixel(a, slot - s * a.slotsPerSample, cam, px, py);
+        pi = (size_t(cam) * a.h + py) * a.w + px;
+      }
+      if (hB == -1) {
+        const V3 emission = shadeMiss(a.sc, a.pc, rd, tex);
+        color += emission * weight;
+        if (firstHitOutputs) {
+          a.albedo[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+          a.normal[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+          a.hitIds[pi] = make_int2(-1, -1);
+          a.hitT[pi] = 0.0f;
+          a.depth[pi] = 0.0f;
+        }
+        a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+      } else {
+        isHit = true;
+        Hit hit;
+        hit.t = hA.x;
+        hit.u = hA.y;
+        hit.v = hA.z;
+        hit.prim = __float_as_int(hA.w);
+        hit.inst = int(uint32_t(hB) & 0x7fffffffu);
+        hit.front = uint32_t(hB) >> 31;
+        if (firstHitOutputs) {
+          const float Px = cadd(ro.x, cmul(rd.x, hit.t)), Py = cadd(ro.y, cmul(rd.y, hit.t)),
+                      Pz = cadd(ro.z, cmul(rd.z, hit.t));
+          const float* vm = a.cams[cam].view;
+          a.hitIds[pi] = make_int2(hit.inst, hit.prim);
+          a.hitT[pi] = hit.t;
+          a.depth[pi] = -cadd(cadd(cadd(cmul(vm[2], Px), cmul(vm[6], Py)), cmul(vm[10], Pz)), vm[14]);
+        }
+        Surface sf;
+        V3 L, w, albedo, emission;
+        if (!shadeSurface(a.sc, hit, ro, rd, seed, sf, L, w, albedo, emission, tex)) {
+          color += emission * weight;  // emissive surface ends the path (rchit:330-334)
+          if (firstHitOutputs) {
+            a.albedo[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+            a.normal[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+          }
+          a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+        } else {
+          if (firstHitOutputs) {
+            a.albedo[pi] = make_float4(albedo.x, albedo.y, albedo.z, 1.f);
+            a.normal[pi] = make_float4(sf.N.x, sf.N.y, sf.N.z, 1.f);
+          }
+          color += mk3(0.0f) * weight;  // ray.emission = 0 (rgen:109 keeps NaN/Inf semantics)
+          weight *= w;                  // rgen:110; the NEE sum is scaled by the post-BSDF weight
+          // next extension ray (rchit:462-463); the occlusion rays share its origin
+          a.b.rayO[slot] = make_float4(sf.worldPos.x, sf.worldPos.y, sf.worldPos.z, 0.0f);
+          a.b.rayD[slot] = make_float4(L.x, L.y, L.z, 0.0f);
+          int k = 0;
+          V3 Ls, le;
+          float maxDist;
+          if (nextLight(a.sc, sf, seed, k, Ls, maxDist, le, tex)) {
+            uint32_t specSeed = seed;
+            const V3 contrib = calcDirect(sf, Ls, le, specSeed);
+            a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
+            a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
+            if (MULTI) storeCtx(a.b.ctx + size_t(6) * slot, sf, k, mk3(0.0f));
+            a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
+            a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+            toShadow = true;
+          } else {
+            // no light needs a ray: shadow_color = 0, advance right away
+            color += mk3(0.0f) * weight;
+            toNext = advancePath(a.pc, depth, weight, seed);
+            a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
+            a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+          }
+        }
+      }
+      texTotal += tex;
+    }
+    queueAppend(a.b.queue[q ^ 1], a.b.counts + (q ^ 1), toNext, slot);
+    queueAppend(a.b.shadowQueue[0], a.b.counts + 2, toShadow, slot);
+    countAdd(a.counters + 3, isHit);
+  }
+  if (DETAIL) atomicAdd(a.counters + 7, texTotal);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sq: which shadow queue to read; q: the extension queue being filled for the next bounce.
+template <bool MULTI, bool DETAIL>
+__global__ void __launch_bounds__(128) k_wf_shadow(WfArgs a, int sq, int qNext, uint32_t depth) {
+  const uint32_t count = a.b.counts[2 + sq];
+  const uint32_t* __restrict__ queue = a.b.shadowQueue[sq];
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + 2, (unsigned long long)count);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  TravCounters tc{0, 0, 0};
+  unsigned long long texTotal = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < count;
+    bool toNext = false, toShadow = false;
+    uint32_t slot = 0;
+    if (valid) {
+      slot = queue[i];
+      const float4 o4 = a.b.rayO[slot], l4 = a.b.shadowL[slot];
+      Hit sh;
+      const bool occluded = traverse<true, DETAIL>(a.sc, mk3(o4.x, o4.y, o4.z), mk3(l4.x, l4.y, l4.z), 0.001f, l4.w,
+                                                   0u, sh, tc);
+      const float4 sw = a.b.stateW[slot], sc4 = a.b.stateC[slot], spec = a.b.shadowC[slot];
+      V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
+      uint32_t seed = __float_as_uint(sw.w);
+      V3 shadowColor = mk3(0.0f);
+      if (!occluded) {
+        shadowColor = mk3(spec.x, spec.y, spec.z);
+        seed = __float_as_uint(spec.w);
+      }
+      bool pending = false;
+      if (MULTI) {
+        Surface sf;
+        int k;
+        V3 acc;
+        loadCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);
+        sf.worldPos = mk3(o4.x, o4.y, o4.z);
+        acc += shadowColor;
+        k++;
+        V3 Ls, le;
+        float maxDist;
+        uint32_t tex = 0;
+        if (nextLight(a.sc, sf, seed, k, Ls, maxDist, le, tex)) {
+          uint32_t specSeed = seed;
+          const V3 contrib = calcDirect(sf, Ls, le, specSeed);
+          a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
+          a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
+          storeCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);
+          a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
+          pending = true;
+          toShadow = true;
+        }
+        texTotal += tex;
+        shadowColor = acc;
+      }
+      if (!pending) {
+        color += shadowColor * weight;  // rgen:111
+        toNext = advancePath(a.pc, depth, weight, seed);
+        a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
+        a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+      }
+    }
+    queueAppend(a.b.queue[qNext], a.b.counts + qNext, toNext, slot);
+    if (MULTI) queueAppend(a.b.shadowQueue[sq ^ 1], a.b.counts + 2 + (sq ^ 1), toShadow, slot);
+  }
+  if (DETAIL) {
+    atomicAdd(a.counters + 4, (unsigned long long)tc.nodes);
+    atomicAdd(a.counters + 5, (unsigned long long)tc.tris);
+    atomicAdd(a.counters + 6, (unsigned long long)tc.insts);
+    atomicAdd(a.counters + 7, texTotal);
+  }
+}
+
+__global__ void k_wf_clear_count(uint32_t* c) { *c = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// colours of the batch's samples are added in sample order, continuing the running sum of earlier
+// batches, so the float association equals the reference's `colors += color` loop (rgen:140).
+__global__ void __launch_bounds__(256) k_wf_finish(WfArgs a) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.slotsPerSample) return;
+  uint32_t cam, x, y;
+  slotToPixel(a, slot, cam, x, y);
+  if (x >= a.w || y >= a.h) return;
+  const size_t pi = (size_t(cam) * a.h + y) * a.w + x;
+  V3 colors = mk3(0.0f);
+  if (a.batchBegin != a.firstSample) {
+    const float4 s = a.sum[pi];
+    colors = mk3(s.x, s.y, s.z);
+  }
+  for (uint32_t s = 0; s < a.batchCount; s++) {
+    const float4 c = a.b.stateC[size_t(s) * a.slotsPerSample + slot];
+    colors += mk3(c.x, c.y, c.z);
+  }
+  a.sum[pi] = make_float4(colors.x, colors.y, colors.z, float(a.batchBegin + a.batchCount - a.firstSample));
+}
+
+}  // namespace kf

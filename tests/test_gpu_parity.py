@@ -143,3 +143,31 @@ def test_error_behaviour(rt):
         ctx.set_instances(np.zeros(3, wire.INSTANCE))
     assert e.value.code == 3
     ctx.close()
+
+
+def test_megakernel_scheduler_still_matches(rt, orc_mod, monkeypatch):
+    """The round-1 megakernel (KFRT_SCHEDULER=mega) is kept for A/B runs; it must obey the same contract."""
+    monkeypatch.setenv("KFRT_SCHEDULER", "mega")
+    sc = pyscene.small_scene(seed=8, w=96, h=64, spp=2, depth=5, lights="dir point", textures=True)
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc)
+    parity.assert_hits_bit_exact(got, ref)
+    _check_radiance(got, ref, 2)
+    assert int(ctx.counters()["kernelLaunches"]) == 1
+    ctx.close()
+
+
+def test_small_batches_equal_one_batch(rt, orc_mod, monkeypatch):
+    """Wavefront batching must not change the result: sample order of the per-pixel sum is preserved."""
+    sc = pyscene.small_scene(seed=9, w=64, h=40, spp=5, depth=4, lights="dir")
+    ctx, orc = _pair(sc, rt, orc_mod)
+    cams = np.array(sc.cams, wire.CAMERA)
+    ctx.render(cams, sc.w, sc.h, sc.pc, clock_base=2)
+    one = ctx.download_aux(wire.AUX_SUM32F).copy()
+    ctx.close()
+    monkeypatch.setenv("KFRT_BATCH_SLOTS", str(64 * 40 * 2))  # two samples per batch -> 3 batches
+    ctx2 = rt.Context(0)
+    sc.upload(ctx2)
+    ctx2.render(cams, sc.w, sc.h, sc.pc, clock_base=2)
+    assert np.array_equal(ctx2.download_aux(wire.AUX_SUM32F).view(np.uint32), one.view(np.uint32))
+    ctx2.close()
