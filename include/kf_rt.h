@@ -137,7 +137,10 @@ typedef struct KfrtCounters {
   uint64_t instanceVisits; /* TLAS leaf entries (ray transformed into a BLAS) (detail) */
   uint64_t textureFetches; /* bilinear texture lookups (detail) */
   uint64_t kernelLaunches; /* CUDA kernels launched by the last kfrtRender/kfrtResolve */
-  uint64_t reserved[7];
+  uint64_t shadowNodeVisits;     /* the occlusion-ray share of nodeVisits (detail) */
+  uint64_t shadowTriangleTests;  /* the occlusion-ray share of triangleTests (detail) */
+  uint64_t shadowInstanceVisits; /* the occlusion-ray share of instanceVisits (detail) */
+  uint64_t reserved[4];
 } KfrtCounters;
 
 /* BVH statistics for the roofline accounting in DESIGN.md. */

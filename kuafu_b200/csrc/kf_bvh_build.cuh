@@ -399,7 +399,17 @@ KF_D uint32_t exponentFor(float extent) {
 }
 
 // Quantises the member boxes of one wide node.  slotBox[s] is ignored where slotUsed bit s is 0.
-KF_D void quantiseNode(Node8& nd, const Box6& nb, const Box6* slotBox, uint32_t slotUsed) {
+// The grid origin sits a little outside the node box and planes are rounded outward with a guard of
+// 1/128 step, so every stored plane is at least ~0.008 step outside the true one: that margin covers
+// the 2^-9-step rounding of the biased dequantisation in intersectNode() (kf_traverse.cuh).
+KF_D void quantiseNode(Node8& nd, const Box6& nbIn, const Box6* slotBox, uint32_t slotUsed) {
+  Box6 nb = nbIn;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float eps = (nb.hi[k] - nb.lo[k]) * (1.0f / 8192.0f);
+    nb.lo[k] -= eps;
+    nb.hi[k] += eps;
+  }
   nd.px = nb.lo[0];
   nd.py = nb.lo[1];
   nd.pz = nb.lo[2];
@@ -412,6 +422,7 @@ KF_D void quantiseNode(Node8& nd, const Box6& nb, const Box6* slotBox, uint32_t 
   const float isx = 1.0f / __uint_as_float(ex << 23);
   const float isy = 1.0f / __uint_as_float(ey << 23);
   const float isz = 1.0f / __uint_as_float(ez << 23);
+  const float g = 1.0f / 128.0f;
 #pragma unroll
   for (int s = 0; s < 8; s++) {
     if (!((slotUsed >> s) & 1u)) {
@@ -420,12 +431,12 @@ KF_D void quantiseNode(Node8& nd, const Box6& nb, const Box6* slotBox, uint32_t 
       continue;
     }
     const Box6& b = slotBox[s];
-    nd.qlox[s] = uint8_t(fminf(fmaxf(floorf((b.lo[0] - nb.lo[0]) * isx), 0.0f), 255.0f));
-    nd.qloy[s] = uint8_t(fminf(fmaxf(floorf((b.lo[1] - nb.lo[1]) * isy), 0.0f), 255.0f));
-    nd.qloz[s] = uint8_t(fminf(fmaxf(floorf((b.lo[2] - nb.lo[2]) * isz), 0.0f), 255.0f));
-    nd.qhix[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[0] - nb.lo[0]) * isx), 0.0f), 255.0f));
-    nd.qhiy[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[1] - nb.lo[1]) * isy), 0.0f), 255.0f));
-    nd.qhiz[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[2] - nb.lo[2]) * isz), 0.0f), 255.0f));
+    nd.qlox[s] = uint8_t(fminf(fmaxf(floorf((b.lo[0] - nb.lo[0]) * isx - g), 0.0f), 255.0f));
+    nd.qloy[s] = uint8_t(fminf(fmaxf(floorf((b.lo[1] - nb.lo[1]) * isy - g), 0.0f), 255.0f));
+    nd.qloz[s] = uint8_t(fminf(fmaxf(floorf((b.lo[2] - nb.lo[2]) * isz - g), 0.0f), 255.0f));
+    nd.qhix[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[0] - nb.lo[0]) * isx + g), 0.0f), 255.0f));
+    nd.qhiy[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[1] - nb.lo[1]) * isy + g), 0.0f), 255.0f));
+    nd.qhiz[s] = uint8_t(fminf(fmaxf(ceilf((b.hi[2] - nb.lo[2]) * isz + g), 0.0f), 255.0f));
   }
 }
 

@@ -154,7 +154,7 @@ struct KfrtContext {
   DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
   DevBuf<int> wfHitB;
   DevBuf<uint32_t> wfQueue0, wfQueue1, wfShadowQ0, wfShadowQ1, wfCounts;
-  int gridExtend[2] = {0, 0}, gridShade[4] = {0, 0, 0, 0}, gridShadow[4] = {0, 0, 0, 0}, gridRaygen = 0;
+  int gridTrace[4] = {0, 0, 0, 0}, gridShade[4] = {0, 0, 0, 0}, gridShadow[4] = {0, 0, 0, 0}, gridRaygen = 0;
   KfrtCounters lastCounters{};
 };
 
@@ -938,19 +938,21 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   KF_CUDA(ctx, ctx->wfQueue1.ensure(slots));
   KF_CUDA(ctx, ctx->wfShadowQ0.ensure(slots));
   if (multi) KF_CUDA(ctx, ctx->wfShadowQ1.ensure(slots));
-  KF_CUDA(ctx, ctx->wfCounts.ensure(4));
+  KF_CUDA(ctx, ctx->wfCounts.ensure(8));
   if (!ctx->gridRaygen) {
     ctx->gridRaygen = persistentGrid(ctx, k_wf_raygen, 256);
-    ctx->gridExtend[0] = persistentGrid(ctx, k_wf_extend<false>, 128);
-    ctx->gridExtend[1] = persistentGrid(ctx, k_wf_extend<true>, 128);
+    ctx->gridTrace[0] = persistentGrid(ctx, k_wf_trace<false, false>, 128);
+    ctx->gridTrace[1] = persistentGrid(ctx, k_wf_trace<false, true>, 128);
+    ctx->gridTrace[2] = persistentGrid(ctx, k_wf_trace<true, false>, 128);
+    ctx->gridTrace[3] = persistentGrid(ctx, k_wf_trace<true, true>, 128);
     ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, 128);
     ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, 128);
     ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, 128);
     ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true>, 128);
-    ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow<false, false>, 128);
-    ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow<false, true>, 128);
-    ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow<true, false>, 128);
-    ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow<true, true>, 128);
+    ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow_resolve<false, false>, 128);
+    ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow_resolve<false, true>, 128);
+    ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow_resolve<true, false>, 128);
+    ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow_resolve<true, true>, 128);
   }
   WfArgs a;
   a.sc = ra.sc;
@@ -991,13 +993,30 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   for (uint32_t b0 = ra.s0; b0 < ra.s1; b0 += batch) {
     a.batchBegin = b0;
     a.batchCount = std::min(batch, ra.s1 - b0);
-    KF_CUDA(ctx, cudaMemsetAsync(a.b.counts, 0, 4 * sizeof(uint32_t), st));
+    KF_CUDA(ctx, cudaMemsetAsync(a.b.counts, 0, 8 * sizeof(uint32_t), st));
     k_wf_raygen<<<ctx->gridRaygen, 256, 0, st>>>(a);
     ctx->launches++;
     for (uint32_t depth = 0; depth <= ra.pc.maxPathDepth; depth++) {
       const int q = int(depth & 1u);
-      if (d) k_wf_extend<true><<<ctx->gridExtend[1], 128, 0, st>>>(a, q);
-      else k_wf_extend<false><<<ctx->gridExtend[0], 128, 0, st>>>(a, q);
+      // closest hit of the extension queue; resets the queues the later stages of this bounce fill
+      TraceArgs te;
+      te.sc = a.sc;
+      te.queue = a.b.queue[q];
+      te.count = a.b.counts + q;
+      te.fetch = a.b.counts + 4;
+      te.rayO = a.b.rayO;
+      te.rayD = a.b.rayD;
+      te.seedSrc = a.b.stateW;
+      te.hitA = a.b.hitA;
+      te.hitB = a.b.hitB;
+      te.clear0 = a.b.counts + (q ^ 1);
+      te.clear1 = a.b.counts + 2;
+      te.clear2 = a.b.counts + 3;
+      te.counters = a.counters;
+      te.rayCounter = 1;
+      te.detailBase = 4;
+      if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
+      else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
       switch (variant) {
         case 0: k_wf_shade<false, false><<<ctx->gridShade[0], 128, 0, st>>>(a, q, depth); break;
         case 1: k_wf_shade<false, true><<<ctx->gridShade[1], 128, 0, st>>>(a, q, depth); break;
@@ -1008,13 +1027,23 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       const uint32_t rounds = ctx->nLightSlots;
       for (uint32_t l = 0; l < rounds; l++) {
         const int sq = multi ? int(l & 1u) : 0;
+        TraceArgs ts = te;
+        ts.queue = a.b.shadowQueue[sq];
+        ts.count = a.b.counts + 2 + sq;
+        ts.fetch = a.b.counts + 5;
+        ts.rayD = a.b.shadowL;
+        ts.clear0 = ts.clear1 = ts.clear2 = nullptr;
+        ts.rayCounter = 2;
+        ts.detailBase = 8;
+        if (d) k_wf_trace<true, true><<<ctx->gridTrace[3], 128, 0, st>>>(ts);
+        else k_wf_trace<true, false><<<ctx->gridTrace[2], 128, 0, st>>>(ts);
         switch (variant) {
-          case 0: k_wf_shadow<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          case 1: k_wf_shadow<false, true><<<ctx->gridShadow[1], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          case 2: k_wf_shadow<true, false><<<ctx->gridShadow[2], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          default: k_wf_shadow<true, true><<<ctx->gridShadow[3], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          case 0: k_wf_shadow_resolve<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          case 1: k_wf_shadow_resolve<false, true><<<ctx->gridShadow[1], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          case 2: k_wf_shadow_resolve<true, false><<<ctx->gridShadow[2], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
+          default: k_wf_shadow_resolve<true, true><<<ctx->gridShadow[3], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
         }
-        ctx->launches++;
+        ctx->launches += 2;
         if (multi && l + 1 < rounds) {
           k_wf_clear_count<<<1, 1, 0, st>>>(a.b.counts + 2 + sq);
           ctx->launches++;
@@ -1233,9 +1262,12 @@ int kfrtGetCounters(KfrtContext* ctx, KfrtCounters* out) {
   out->extensionRays = h[1];
   out->shadowRays = h[2];
   out->extensionHits = h[3];
-  out->nodeVisits = h[4];
-  out->triangleTests = h[5];
-  out->instanceVisits = h[6];
+  out->nodeVisits = h[4] + h[8];
+  out->triangleTests = h[5] + h[9];
+  out->instanceVisits = h[6] + h[10];
+  out->shadowNodeVisits = h[8];
+  out->shadowTriangleTests = h[9];
+  out->shadowInstanceVisits = h[10];
   out->textureFetches = h[7];
   out->kernelLaunches = ctx->launches;
   return KFRT_OK;

@@ -1,0 +1,255 @@
+// kf_trace.cuh -- persistent-warp ray traversal stage of the wavefront scheduler (replaces
+// traceRayEXT and the driver/RT-core traversal behind it: reference PathTrace.rgen:97-107 closest
+// hit, PathTrace.rchit:186-197 occlusion).
+//
+// One lane walks one ray through the two-level compressed 8-wide BVH, but lanes are *persistent*:
+// a lane whose ray has terminated does not wait for the slowest ray of its warp, it takes the next
+// ray from the stage queue (one warp-aggregated atomic per refill).  With incoherent bounce rays the
+// per-ray traversal length varies by an order of magnitude, so this is what keeps lanes busy.
+//
+// Every lane iteration is one traversal step:
+//   [node]      pop the nearest pending child of the current node group, fetch its 80-byte node
+//               (5 x 16 B loads), slab-test its 8 quantised child boxes
+//   [triangle]  (bottom level) Moller-Trumbore on the leaf triangles of the current group
+//   [instance]  (top level) enter the next instance of the current leaf group: 64-byte record,
+//               world -> object ray transform
+//   [pop]       next group from the stack; a sentinel entry returns from the bottom level
+//
+// Results do not depend on traversal order: boxes are conservative and equal-t ties resolve to the
+// lowest (instance, primitive) pair (oracle deviation D3), so hit buffers stay bit-exact with the
+// CPU oracle whatever the scheduling.
+#pragma once
+
+#include "kf_common.cuh"
+#include "kf_traverse.cuh"
+
+namespace kf {
+
+#define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
+
+struct TraceArgs {
+  SceneDev sc;
+  const uint32_t* queue;     // slots to trace
+  const uint32_t* count;     // number of queued slots (device)
+  uint32_t* fetch;           // next queue position to hand out (zeroed by an earlier stage)
+  const float4* rayO;        // origin.xyz per slot
+  const float4* rayD;        // direction.xyz (+ tmax in .w for occlusion rays) per slot
+  const float4* seedSrc;     // stateW: .w = ray seed bits (closest hit, non-opaque geometry only)
+  float4* hitA;              // closest hit: t, u, v, prim bits
+  int* hitB;                 // closest hit: inst | front << 31, -1 on miss; occlusion: 1 occluded / 0
+  uint32_t* clear0;          // counters this stage resets for later stages (may be null)
+  uint32_t* clear1;
+  uint32_t* clear2;
+  unsigned long long* counters;
+  int rayCounter;            // counters[] index that receives the number of rays of this stage
+  int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
+};
+
+// Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
+// SkipClosestHitShader) for every ray of the queue.
+template <bool ANY, bool DETAIL>
+__global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
+  const uint32_t count = *a.count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.clear0) *a.clear0 = 0;
+    if (a.clear1) *a.clear1 = 0;
+    if (a.clear2) *a.clear2 = 0;
+    atomicAdd(a.counters + a.rayCounter, (unsigned long long)count);
+  }
+  const SceneDev& sc = a.sc;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t laneLt = (1u << lane) - 1u;
+  const float tmin = 0.001f;
+
+  TravCounters tc{0, 0, 0};
+  uint2 stack[KF_STACK];
+  int sp = 0;
+  bool active = false, exhausted = false;
+  uint32_t slot = 0;
+  V3 o = mk3(0.0f), d = mk3(0.0f);
+  RaySetup r = setupRay(o, mk3(1.0f));
+  Hit hit;
+  hit.t = 0.0f; hit.u = hit.v = 0.0f; hit.inst = hit.prim = -1; hit.front = 0;
+  const Node8* nodes = sc.tlasNodes;
+  const Tri48* tris = nullptr;
+  bool inBlas = false, nonOpaque = false;
+  int32_t curInst = -1;
+  uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+
+  for (;;) {
+    // ---- refill: lanes without a ray take consecutive queue positions -------------------------
+    const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+    if (idle) {
+      if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= KF_REFILL_IDLE)) {
+        const uint32_t want = uint32_t(__popc(idle));
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.fetch, want);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!active) {
+          const uint32_t qi = base + uint32_t(__popc(idle & laneLt));
+          if (qi < count) {
+            slot = a.queue[qi];
+            const float4 o4 = a.rayO[slot], d4 = a.rayD[slot];
+            o = mk3(o4.x, o4.y, o4.z);
+            d = mk3(d4.x, d4.y, d4.z);
+            hit.t = ANY ? d4.w : 10000.0f;
+            hit.u = hit.v = 0.0f;
+            hit.inst = -1;
+            hit.prim = -1;
+            hit.front = 0;
+            r = setupRay(o, d);
+            nodes = sc.tlasNodes;
+            inBlas = false;
+            nonOpaque = false;
+            curInst = -1;
+            sp = 0;
+            ng = make_uint2(0u, sc.tlasNodes ? 0x80000000u : 0u);
+            tg = make_uint2(0u, 0u);
+            active = true;
+          }
+        }
+        if (base + want >= count) exhausted = true;
+      }
+      if (exhausted && __ballot_sync(0xffffffffu, active) == 0u) break;
+    }
+    if (!active) continue;
+
+    // ---- one traversal step ---------------------------------------------------------------------
+    bool finished = false;
+    if (ng.y & 0xff000000u) {
+      const uint32_t hits = ng.y;
+      const int p = 31 - __clz(hits);
+      ng.y &= ~(1u << p);
+      if (ng.y & 0xff000000u) {
+        if (sp < KF_STACK) stack[sp++] = ng;
+      }
+      const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;
+      const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
+      uint32_t childBase, primBase, imask;
+      const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);
+      if (DETAIL) tc.nodes++;
+      ng = make_uint2(childBase, (hm & 0xff000000u) | imask);
+      tg = make_uint2(primBase, hm & 0x00ffffffu);
+    } else {
+      tg = ng;  // a popped primitive group (or nothing)
+      ng = make_uint2(0u, 0u);
+    }
+
+    bool entered = false;
+    if (inBlas) {
+      while (tg.y) {
+        const int b = __ffs(tg.y) - 1;
+        tg.y &= tg.y - 1;
+        const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
+        const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+        if (DETAIL) tc.tris++;
+        // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
+        const V3 dd = mk3(r.dx, r.dy, r.dz);
+        const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
+        const V3 pv = ccross(dd, E2);
+        const float det = cdot(E1, pv);
+        if (det == 0.0f) continue;
+        const float inv = cdiv(1.0f, det);
+        const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(v0.x, v0.y, v0.z));
+        const float u = cmul(cdot(tv, pv), inv);
+        if (!(u >= 0.0f && u <= 1.0f)) continue;
+        const V3 qv = ccross(tv, E1);
+        const float v = cmul(cdot(dd, qv), inv);
+        if (!(v >= 0.0f && cadd(u, v) <= 1.0f)) continue;
+        const float t = cmul(cdot(E2, qv), inv);
+        if (!(t > tmin)) continue;
+        const int32_t prim = int32_t(__float_as_uint(v0.w));
+        const bool closer = t < hit.t || (t == hit.t && hit.inst >= 0 &&
+                                          (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim)));
+        if (!closer) continue;
+        if (!ANY && nonOpaque) {
+          const uint32_t g = sc.instSsbo[curInst].geometryIndex;
+          const uint32_t mi = __ldg(sc.geoms[g].matIndex + prim);
+          const float alpha = sc.mats[mi].alpha;
+          if (alpha == 0.0f) continue;
+          const uint32_t seed = __float_as_uint(a.seedSrc[slot].w);
+          if (anyHitRnd(seed, uint32_t(curInst), uint32_t(prim)) > alpha) continue;
+        }
+        hit.t = t;
+        hit.u = u;
+        hit.v = v;
+        hit.inst = curInst;
+        hit.prim = prim;
+        hit.front = det > 0.0f ? 1u : 0u;
+        if (ANY) {
+          finished = true;
+          break;
+        }
+      }
+    } else {
+      while (tg.y) {
+        const int b = __ffs(tg.y) - 1;
+        tg.y &= tg.y - 1;
+        const uint32_t ii = __ldg(sc.tlasInstIdx + tg.x + b);
+        const float4* ip = reinterpret_cast<const float4*>(sc.inst + ii);
+        const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+        const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
+        if (ptrs.x == 0ull) continue;
+        if (DETAIL) tc.insts++;
+        // save what is left of this TLAS node, then the marker that brings us back
+        if (tg.y && sp < KF_STACK) stack[sp++] = tg;
+        if ((ng.y & 0xff000000u) && sp < KF_STACK) stack[sp++] = ng;
+        if (sp < KF_STACK) stack[sp++] = make_uint2(0xffffffffu, 0u);
+        // world -> object (contract arithmetic, oracle traceInstance())
+        V3 oo, od;
+        oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
+        oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
+        oo.z = cadd(cdot3(r2.x, r2.y, r2.z, o.x, o.y, o.z), r2.w);
+        od.x = cdot3(r0.x, r0.y, r0.z, d.x, d.y, d.z);
+        od.y = cdot3(r1.x, r1.y, r1.z, d.x, d.y, d.z);
+        od.z = cdot3(r2.x, r2.y, r2.z, d.x, d.y, d.z);
+        r = setupRay(oo, od);
+        nodes = reinterpret_cast<const Node8*>(ptrs.x);
+        nonOpaque = (ptrs.y & 1ull) != 0;
+        tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
+        curInst = int32_t(ii);
+        inBlas = true;
+        ng = make_uint2(0u, 0x80000000u);
+        tg = make_uint2(0u, 0u);
+        entered = true;
+        break;
+      }
+    }
+
+    if (!finished && !entered && !(ng.y & 0xff000000u)) {
+      for (;;) {
+        if (sp == 0) {
+          finished = true;
+          break;
+        }
+        const uint2 e = stack[--sp];
+        if (e.y == 0u) {  // sentinel: back to the top level
+          r = setupRay(o, d);
+          nodes = sc.tlasNodes;
+          inBlas = false;
+          continue;
+        }
+        ng = e;
+        break;
+      }
+    }
+
+    if (finished) {
+      if (ANY) {
+        a.hitB[slot] = hit.inst >= 0 ? 1 : 0;
+      } else {
+        a.hitA[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.prim));
+        a.hitB[slot] = hit.inst < 0 ? -1 : int(uint32_t(hit.inst) | (hit.front << 31));
+      }
+      active = false;
+    }
+  }
+
+  if (DETAIL) {
+    atomicAdd(a.counters + a.detailBase + 0, (unsigned long long)tc.nodes);
+    atomicAdd(a.counters + a.detailBase + 1, (unsigned long long)tc.tris);
+    atomicAdd(a.counters + a.detailBase + 2, (unsigned long long)tc.insts);
+  }
+}
+
+}  // namespace kf

@@ -37,7 +37,12 @@ KF_D RaySetup setupRay(V3 o, V3 d) {
   return r;
 }
 
-KF_D float byteToFloat(uint32_t w, int i) { return float((w >> (8 * i)) & 0xffu); }
+// Quantised plane byte j of word w as the float 1 + q * 2^-15: one PRMT drops the byte into the
+// second mantissa byte of 1.0f, so the dequantisation never touches the (quarter-rate) int->float
+// conversion pipe.  t = f * A + B with A = 2^15 * scale * idir, B = (origin term) - A.
+KF_D float planeFloat(uint32_t w, int j) {
+  return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
+}
 
 // Intersects the 8 quantised child boxes of `node`; returns the CWBVH hit mask:
 // bits 24..31 internal children by traversal priority, bits 0..23 leaf primitives.
@@ -52,13 +57,14 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
   childBase = n1.x;
   primBase = n1.y;
   imask = n0.w >> 24;
-  const float sx = __uint_as_float((n0.w & 0xffu) << 23);
-  const float sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23);
-  const float sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+  // per-axis grid step 2^(e-127), pre-multiplied by 2^15 (see planeFloat)
+  const float sx = __uint_as_float(((n0.w & 0xffu) + 15u) << 23);
+  const float sy = __uint_as_float((((n0.w >> 8) & 0xffu) + 15u) << 23);
+  const float sz = __uint_as_float((((n0.w >> 16) & 0xffu) + 15u) << 23);
   const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
-  const float bx = (__uint_as_float(n0.x) - r.ox) * r.ix;
-  const float by = (__uint_as_float(n0.y) - r.oy) * r.iy;
-  const float bz = (__uint_as_float(n0.z) - r.oz) * r.iz;
+  const float bx = (__uint_as_float(n0.x) - r.ox) * r.ix - ax;
+  const float by = (__uint_as_float(n0.y) - r.oy) * r.iy - ay;
+  const float bz = (__uint_as_float(n0.z) - r.oz) * r.iz - az;
   // near/far plane words per axis (two words = 8 children)
   const bool nx = r.ix < 0.0f, ny = r.iy < 0.0f, nz = r.iz < 0.0f;
   const uint32_t lox[2] = {n2.x, n2.y}, loy[2] = {n2.z, n2.w}, loz[2] = {n3.x, n3.y};
@@ -73,12 +79,12 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t m = (meta[h] >> (8 * j)) & 0xffu;
-      const float t0x = fmaf(byteToFloat(nearx, j), ax, bx);
-      const float t0y = fmaf(byteToFloat(neary, j), ay, by);
-      const float t0z = fmaf(byteToFloat(nearz, j), az, bz);
-      const float t1x = fmaf(byteToFloat(farx, j), ax, bx);
-      const float t1y = fmaf(byteToFloat(fary, j), ay, by);
-      const float t1z = fmaf(byteToFloat(farz, j), az, bz);
+      const float t0x = fmaf(planeFloat(nearx, j), ax, bx);
+      const float t0y = fmaf(planeFloat(neary, j), ay, by);
+      const float t0z = fmaf(planeFloat(nearz, j), az, bz);
+      const float t1x = fmaf(planeFloat(farx, j), ax, bx);
+      const float t1y = fmaf(planeFloat(fary, j), ay, by);
+      const float t1z = fmaf(planeFloat(farz, j), az, bz);
       const float t0 = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       const float t1 = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
       if (m != 0 && t0 <= t1) {

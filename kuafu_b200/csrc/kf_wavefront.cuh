@@ -6,11 +6,12 @@
 //
 //   k_wf_raygen            camera ray + RNG seeds, path state, queue 0
 //   for depth = 0 .. maxPathDepth:
-//     k_wf_extend          closest hit of every queued ray            (traverse<false>)
+//     k_wf_trace<false>    closest hit of every queued ray            (kf_trace.cuh, persistent lanes)
 //     k_wf_shade           miss / emissive -> path ends; surface -> BSDF sample, first light that
 //                          needs an occlusion ray (speculative contribution), or advance directly
-//     k_wf_shadow (x L)    occlusion ray (traverse<true>), resolve the light, walk to the next light
-//                          (multi-light scenes), then advance: Russian roulette, enqueue next bounce
+//     k_wf_trace<true>     occlusion ray of every queued light sample (x L light rounds)
+//     k_wf_shadow_resolve  commit the light if unoccluded, walk to the next light (multi-light
+//                          scenes), then advance: Russian roulette, enqueue next bounce
 //   k_wf_finish            per pixel: add the S sample colours in sample order onto the sum buffer
 //
 // The per-path LCG stream is consumed in exactly the reference order: lobe choice, lobe sample,
@@ -21,6 +22,7 @@
 
 #include "kf_common.cuh"
 #include "kf_shade.cuh"
+#include "kf_trace.cuh"
 #include "kf_traverse.cuh"
 
 namespace kf {
@@ -38,7 +40,7 @@ struct WfBuffers {
   float4* ctx;      // 6 per slot (multi-light): N|f, V|a2, diffuse|isInside, specular|k, transmission|-, shadowAcc|-
   uint32_t* queue[2];
   uint32_t* shadowQueue[2];
-  uint32_t* counts;  // [0..1] extension queue sizes, [2..3] shadow queue sizes
+  uint32_t* counts;  // [0..1] extension queue sizes, [2..3] shadow queue sizes, [4] closest-hit / [5] occlusion fetch cursor
 };
 
 struct WfArgs {
@@ -124,35 +126,6 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-template <bool DETAIL>
-__global__ void __launch_bounds__(128) k_wf_extend(WfArgs a, int q) {
-  const uint32_t count = a.b.counts[q];
-  const uint32_t* __restrict__ queue = a.b.queue[q];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.b.counts[q ^ 1] = 0;  // next extension queue and both shadow queues are empty during this stage
-    a.b.counts[2] = 0;
-    a.b.counts[3] = 0;
-    atomicAdd(a.counters + 1, (unsigned long long)count);
-  }
-  TravCounters tc{0, 0, 0};
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const uint32_t slot = queue[i];
-    const float4 o = a.b.rayO[slot], d = a.b.rayD[slot];
-    const uint32_t seed = __float_as_uint(a.b.stateW[slot].w);
-    Hit hit;
-    traverse<false, DETAIL>(a.sc, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), 0.001f, 10000.0f, seed, hit, tc);
-    a.b.hitA[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.prim));
-    a.b.hitB[slot] = hit.inst < 0 ? -1 : int(uint32_t(hit.inst) | (hit.front << 31));
-  }
-  if (DETAIL) {
-    atomicAdd(a.counters + 4, (unsigned long long)tc.nodes);
-    atomicAdd(a.counters + 5, (unsigned long long)tc.tris);
-    atomicAdd(a.counters + 6, (unsigned long long)tc.insts);
-  }
-}
-
 // Russian roulette and hand-over to the next bounce (reference PathTrace.rgen:119-138).
 // Returns true when the path continues.
 KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, uint32_t& seed) {
@@ -195,6 +168,10 @@ __global__ void __launch_bounds__(128) k_wf_shade(WfArgs a, int q, uint32_t dept
   const uint32_t* __restrict__ queue = a.b.queue[q];
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.b.counts[4] = 0;  // fetch cursors of the next closest-hit / occlusion stages
+    a.b.counts[5] = 0;
+  }
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
     const uint32_t i = base + threadIdx.x;
     const bool valid = i < count;
@@ -298,12 +275,11 @@ __global__ void __launch_bounds__(128) k_wf_shade(WfArgs a, int q, uint32_t dept
 // ---------------------------------------------------------------------------------------------
 // sq: which shadow queue to read; q: the extension queue being filled for the next bounce.
 template <bool MULTI, bool DETAIL>
-__global__ void __launch_bounds__(128) k_wf_shadow(WfArgs a, int sq, int qNext, uint32_t depth) {
+__global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int qNext, uint32_t depth) {
   const uint32_t count = a.b.counts[2 + sq];
   const uint32_t* __restrict__ queue = a.b.shadowQueue[sq];
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + 2, (unsigned long long)count);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[5] = 0;  // occlusion fetch cursor of the next round
   const uint32_t stride = gridDim.x * blockDim.x;
-  TravCounters tc{0, 0, 0};
   unsigned long long texTotal = 0;
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
     const uint32_t i = base + threadIdx.x;
@@ -312,10 +288,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(WfArgs a, int sq, int qNext, 
     uint32_t slot = 0;
     if (valid) {
       slot = queue[i];
-      const float4 o4 = a.b.rayO[slot], l4 = a.b.shadowL[slot];
-      Hit sh;
-      const bool occluded = traverse<true, DETAIL>(a.sc, mk3(o4.x, o4.y, o4.z), mk3(l4.x, l4.y, l4.z), 0.001f, l4.w,
-                                                   0u, sh, tc);
+      const bool occluded = a.b.hitB[slot] != 0;  // written by k_wf_trace<true>
       const float4 sw = a.b.stateW[slot], sc4 = a.b.stateC[slot], spec = a.b.shadowC[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
       uint32_t seed = __float_as_uint(sw.w);
@@ -330,6 +303,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(WfArgs a, int sq, int qNext, 
         int k;
         V3 acc;
         loadCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);
+        const float4 o4 = a.b.rayO[slot];
         sf.worldPos = mk3(o4.x, o4.y, o4.z);
         acc += shadowColor;
         k++;
@@ -359,12 +333,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow(WfArgs a, int sq, int qNext, 
     queueAppend(a.b.queue[qNext], a.b.counts + qNext, toNext, slot);
     if (MULTI) queueAppend(a.b.shadowQueue[sq ^ 1], a.b.counts + 2 + (sq ^ 1), toShadow, slot);
   }
-  if (DETAIL) {
-    atomicAdd(a.counters + 4, (unsigned long long)tc.nodes);
-    atomicAdd(a.counters + 5, (unsigned long long)tc.tris);
-    atomicAdd(a.counters + 6, (unsigned long long)tc.insts);
-    atomicAdd(a.counters + 7, texTotal);
-  }
+  if (DETAIL && MULTI) atomicAdd(a.counters + 7, texTotal);
 }
 
 __global__ void k_wf_clear_count(uint32_t* c) { *c = 0; }

@@ -26,7 +26,8 @@ PUSH_CONSTANTS = np.dtype([("clearColor", "<f4", 4), ("frameCount", "<i4"),
 COUNTERS = np.dtype([("paths", "<u8"), ("extensionRays", "<u8"), ("shadowRays", "<u8"),
                      ("extensionHits", "<u8"), ("nodeVisits", "<u8"), ("triangleTests", "<u8"),
                      ("instanceVisits", "<u8"), ("textureFetches", "<u8"), ("kernelLaunches", "<u8"),
-                     ("reserved", "<u8", 7)])
+                     ("shadowNodeVisits", "<u8"), ("shadowTriangleTests", "<u8"), ("shadowInstanceVisits", "<u8"),
+                     ("reserved", "<u8", 4)])
 BVH_STATS = np.dtype([("blasCount", "<u4"), ("instanceCount", "<u4"), ("triangleCount", "<u8"),
                       ("instancedTriangles", "<u8"), ("blasNodeCount", "<u8"),
                       ("tlasNodeCount", "<u8"), ("nodeBytes", "<u4"), ("triangleBytes", "<u4"),

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) into the handful of metrics DESIGN.md / profiles/ quote."""
+import csv, subprocess, sys
+WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__occupancy_limit_registers', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+        'smsp__inst_executed_op_global_ld.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum',
+        'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_lsu.sum']
+def main(path, out=None):
+    txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    h, u = rows[0], rows[1]
+    lines = []
+    for v in rows[2:]:
+        d = dict(zip(h, v))
+        lines.append(f"# {d.get('Kernel Name','?')}")
+        for i, n in enumerate(h):
+            if n in WANT or 'issue_stalled' in n and n.endswith('per_issue_active.ratio') and float(v[i].replace(',', '') or 0) > 0.15:
+                lines.append(f"{n},{v[i]},{u[i]}")
+    s = "\n".join(lines)
+    print(s)
+    if out:
+        open(out, 'w').write(s + "\n")
+if __name__ == '__main__':
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
