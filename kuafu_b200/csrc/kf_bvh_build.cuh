@@ -113,19 +113,22 @@ __global__ void k_init_scene_box(int* sceneBox) {
   else if (threadIdx.x < 6) sceneBox[threadIdx.x] = floatToOrdered(-3.0e38f);
 }
 
-// World->object matrix, world box (from the 8 corners of the BLAS root box) and InstRec of every
-// instance.  The inverse follows the float cofactor contract of oracle affineInverse().
+// World->object matrix and InstRec of every instance (k_instance_setup: one thread per instance) and
+// its world box (k_instance_box: one block per instance, exact over the transformed vertices -- the
+// box of the 8 transformed corners of the BLAS root box is up to 5x larger in volume for a rotated
+// round object, and every false box hit costs a ray transform plus a BLAS root visit).
+// The inverse follows the float cofactor contract of oracle affineInverse().
 struct BlasInfo {
   const Node8* nodes;
   const Tri48* tris;
+  const KfrtVertex* verts;
   float box[6];
   uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque
-  uint32_t pad;
+  uint32_t nVerts;
 };
 __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_t n,
                                  const BlasInfo* __restrict__ blas, uint32_t nBlas,
-                                 InstRec* __restrict__ recs, float* __restrict__ primBox,
-                                 int* __restrict__ sceneBox) {
+                                 InstRec* __restrict__ recs) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* m = insts[i].transform;
@@ -157,35 +160,74 @@ __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_
 #pragma unroll
     for (int c = 0; c < 4; c++) rec.inv[4 * r + c] = inv[r][c];
   const uint32_t g = insts[i].geometryIndex;
-  Box6 wb;
-  bool usable = g < nBlas && (blas[g].flags & 1u);
+  const bool usable = g < nBlas && (blas[g].flags & 1u);
   if (usable) {
     rec.nodes = blas[g].nodes;
     rec.tris = reinterpret_cast<const Tri48*>(reinterpret_cast<uintptr_t>(blas[g].tris) |
                                               ((blas[g].flags & 2u) ? 1ull : 0ull));
-    boxReset(wb);
-    const float* ob = blas[g].box;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      const float x = (c & 1) ? ob[3] : ob[0];
-      const float y = (c & 2) ? ob[4] : ob[1];
-      const float z = (c & 4) ? ob[5] : ob[2];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const float p = ((m[k] * x + m[4 + k] * y) + m[8 + k] * z) + m[12 + k];
-        wb.lo[k] = fminf(wb.lo[k], p);
-        wb.hi[k] = fmaxf(wb.hi[k], p);
-      }
-    }
-    boxPad(wb);
   } else {
     rec.nodes = nullptr;
     rec.tris = nullptr;
-    // a point box at the first usable... keep it harmless: degenerate box at the origin
+  }
+  recs[i] = rec;
+}
+
+__global__ void __launch_bounds__(128) k_instance_box(const KfrtInstance* __restrict__ insts, uint32_t n,
+                                                      const BlasInfo* __restrict__ blas, uint32_t nBlas,
+                                                      float* __restrict__ primBox, int* __restrict__ sceneBox) {
+  const uint32_t i = blockIdx.x;
+  if (i >= n) return;
+  const float* m = insts[i].transform;
+  const uint32_t g = insts[i].geometryIndex;
+  const bool usable = g < nBlas && (blas[g].flags & 1u);
+  Box6 wb;
+  boxReset(wb);
+  if (usable) {
+    const float m00 = m[0], m10 = m[1], m20 = m[2], m01 = m[4], m11 = m[5], m21 = m[6];
+    const float m02 = m[8], m12 = m[9], m22 = m[10], t0 = m[12], t1 = m[13], t2 = m[14];
+    const KfrtVertex* __restrict__ verts = blas[g].verts;
+    const uint32_t nv = blas[g].nVerts;
+    for (uint32_t v = threadIdx.x; v < nv; v += blockDim.x) {
+      const float x = verts[v].pos[0], y = verts[v].pos[1], z = verts[v].pos[2];
+      const float px = ((m00 * x + m01 * y) + m02 * z) + t0;
+      const float py = ((m10 * x + m11 * y) + m12 * z) + t1;
+      const float pz = ((m20 * x + m21 * y) + m22 * z) + t2;
+      wb.lo[0] = fminf(wb.lo[0], px); wb.hi[0] = fmaxf(wb.hi[0], px);
+      wb.lo[1] = fminf(wb.lo[1], py); wb.hi[1] = fmaxf(wb.hi[1], py);
+      wb.lo[2] = fminf(wb.lo[2], pz); wb.hi[2] = fmaxf(wb.hi[2], pz);
+    }
+  }
+  __shared__ float red[4][6];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wb.lo[k] = fminf(wb.lo[k], __shfl_xor_sync(0xffffffffu, wb.lo[k], o));
+      wb.hi[k] = fmaxf(wb.hi[k], __shfl_xor_sync(0xffffffffu, wb.hi[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      red[threadIdx.x >> 5][k] = wb.lo[k];
+      red[threadIdx.x >> 5][3 + k] = wb.hi[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < 4; w++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      wb.lo[k] = fminf(wb.lo[k], red[w][k]);
+      wb.hi[k] = fmaxf(wb.hi[k], red[w][3 + k]);
+    }
+  if (usable && wb.lo[0] <= wb.hi[0]) {
+    boxPad(wb);
+  } else {
+    // hidden / empty geometry: a harmless degenerate box at the origin (its InstRec has no nodes)
 #pragma unroll
     for (int k = 0; k < 3; k++) wb.lo[k] = wb.hi[k] = 0.0f;
   }
-  recs[i] = rec;
   storeBox(primBox + 6 * i, wb);
   if (sceneBox) {
 #pragma unroll

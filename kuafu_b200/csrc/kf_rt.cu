@@ -149,6 +149,7 @@ struct KfrtContext {
   int numSMs = 148;
   int scheduler = 1;  // 1 wavefront (default), 0 megakernel (KFRT_SCHEDULER=mega; round-1 baseline kept for A/B)
   size_t batchSlotTarget = size_t(16) << 20;
+  int triBatch = KF_TRI_BATCH, instBatch = KF_INST_BATCH;
   size_t wfSlots = 0;
   bool wfMulti = false;
   DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
@@ -315,9 +316,10 @@ static int uploadTables(KfrtContext* ctx) {
     recs[i].flags = (g.opaque ? 1u : 0u) | (g.hide ? 2u : 0u);
     infos[i].nodes = g.nodes;
     infos[i].tris = g.tris;
+    infos[i].verts = g.verts;
+    infos[i].nVerts = g.nVerts;
     std::memcpy(infos[i].box, g.box, sizeof(g.box));
     infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u);
-    infos[i].pad = 0;
   }
   KF_CUDA(ctx, ctx->geomTable.ensure(recs.size()));
   KF_CUDA(ctx, ctx->blasInfo.ensure(infos.size()));
@@ -573,6 +575,8 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
   ctx->stream = ctx->ownStream;
   ctx->numSMs = prop.multiProcessorCount;
   if (const char* e = std::getenv("KFRT_SCHEDULER")) ctx->scheduler = std::strcmp(e, "mega") == 0 ? 0 : 1;
+  if (const char* e = std::getenv("KFRT_TRI_BATCH")) ctx->triBatch = std::atoi(e);
+  if (const char* e = std::getenv("KFRT_INST_BATCH")) ctx->instBatch = std::atoi(e);
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
     if (v > 0) ctx->batchSlotTarget = size_t(v);
@@ -814,8 +818,9 @@ static int instanceSetup(KfrtContext* ctx, bool withSceneBox) {
                                cudaMemcpyHostToDevice, ctx->stream));
   if (withSceneBox) k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
   k_instance_setup<<<gridFor(n, 128), 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p,
-                                                             uint32_t(ctx->geoms.size()), ctx->instRec.p,
-                                                             st.primBox.p, withSceneBox ? st.sceneBox.p : nullptr);
+                                                             uint32_t(ctx->geoms.size()), ctx->instRec.p);
+  k_instance_box<<<n, 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p, uint32_t(ctx->geoms.size()),
+                                             st.primBox.p, withSceneBox ? st.sceneBox.p : nullptr);
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -1015,6 +1020,8 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.counters = a.counters;
       te.rayCounter = 1;
       te.detailBase = 4;
+      te.triBatch = ctx->triBatch;
+      te.instBatch = ctx->instBatch;
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
       else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
       switch (variant) {

@@ -26,6 +26,12 @@
 namespace kf {
 
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
+#ifndef KF_TRI_BATCH
+#define KF_TRI_BATCH 1   // run the triangle phase once this many lanes wait for it
+#endif
+#ifndef KF_INST_BATCH
+#define KF_INST_BATCH 1   // same for the instance-entry phase
+#endif
 
 struct TraceArgs {
   SceneDev sc;
@@ -43,6 +49,7 @@ struct TraceArgs {
   unsigned long long* counters;
   int rayCounter;            // counters[] index that receives the number of rays of this stage
   int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
+  int triBatch, instBatch;   // lanes that must wait for a leaf phase before the warp runs it
 };
 
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
@@ -75,6 +82,32 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
   bool inBlas = false, nonOpaque = false;
   int32_t curInst = -1;
   uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+
+  bool finished = false;
+  // Next group from the lane's stack: a node group goes to ng, a primitive group to tg; a sentinel
+  // (x, 0) returns from the bottom level; an empty stack ends the ray.
+  auto popGroup = [&]() {
+    for (;;) {
+      if (sp == 0) {
+        finished = true;
+        return;
+      }
+      const uint2 e = stack[--sp];
+      if (e.y == 0u) {
+        r = setupRay(o, d);
+        nodes = sc.tlasNodes;
+        inBlas = false;
+        continue;
+      }
+      if (e.y & 0xff000000u) {
+        ng = e;
+      } else {
+        tg = e;
+        ng = make_uint2(0u, 0u);
+      }
+      return;
+    }
+  };
 
   for (;;) {
     // ---- refill: lanes without a ray take consecutive queue positions -------------------------
@@ -112,11 +145,9 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
       }
       if (exhausted && __ballot_sync(0xffffffffu, active) == 0u) break;
     }
-    if (!active) continue;
-
-    // ---- one traversal step ---------------------------------------------------------------------
-    bool finished = false;
-    if (ng.y & 0xff000000u) {
+    // ---- node phase: lanes without pending leaf work take one node step ---------------------
+    finished = false;
+    if (active && tg.y == 0u && (ng.y & 0xff000000u)) {
       const uint32_t hits = ng.y;
       const int p = 31 - __clz(hits);
       ng.y &= ~(1u << p);
@@ -130,66 +161,65 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
       if (DETAIL) tc.nodes++;
       ng = make_uint2(childBase, (hm & 0xff000000u) | imask);
       tg = make_uint2(primBase, hm & 0x00ffffffu);
-    } else {
-      tg = ng;  // a popped primitive group (or nothing)
-      ng = make_uint2(0u, 0u);
     }
+    // ---- pop: lanes with nothing in hand take the next group from their stack ------------------
+    if (active && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
 
-    bool entered = false;
-    if (inBlas) {
-      while (tg.y) {
-        const int b = __ffs(tg.y) - 1;
-        tg.y &= tg.y - 1;
-        const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
-        const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-        if (DETAIL) tc.tris++;
-        // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
-        const V3 dd = mk3(r.dx, r.dy, r.dz);
-        const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
-        const V3 pv = ccross(dd, E2);
-        const float det = cdot(E1, pv);
-        if (det == 0.0f) continue;
-        const float inv = cdiv(1.0f, det);
-        const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(v0.x, v0.y, v0.z));
-        const float u = cmul(cdot(tv, pv), inv);
-        if (!(u >= 0.0f && u <= 1.0f)) continue;
-        const V3 qv = ccross(tv, E1);
-        const float v = cmul(cdot(dd, qv), inv);
-        if (!(v >= 0.0f && cadd(u, v) <= 1.0f)) continue;
-        const float t = cmul(cdot(E2, qv), inv);
-        if (!(t > tmin)) continue;
-        const int32_t prim = int32_t(__float_as_uint(v0.w));
-        const bool closer = t < hit.t || (t == hit.t && hit.inst >= 0 &&
-                                          (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim)));
-        if (!closer) continue;
-        if (!ANY && nonOpaque) {
-          const uint32_t g = sc.instSsbo[curInst].geometryIndex;
-          const uint32_t mi = __ldg(sc.geoms[g].matIndex + prim);
-          const float alpha = sc.mats[mi].alpha;
-          if (alpha == 0.0f) continue;
-          const uint32_t seed = __float_as_uint(a.seedSrc[slot].w);
-          if (anyHitRnd(seed, uint32_t(curInst), uint32_t(prim)) > alpha) continue;
-        }
+    // ---- leaf phases run warp-wide, once enough lanes wait for them (or nobody can step) ------
+    const bool wantLeaf = active && !finished && tg.y != 0u;
+    const uint32_t mTri = __ballot_sync(0xffffffffu, wantLeaf && inBlas);
+    const uint32_t mInst = __ballot_sync(0xffffffffu, wantLeaf && !inBlas);
+    const uint32_t mStep = __ballot_sync(0xffffffffu, active && !finished && tg.y == 0u);
+    const bool runTri = mTri != 0u && (__popc(mTri) >= a.triBatch || mStep == 0u);
+    const bool runInst = mInst != 0u && (__popc(mInst) >= a.instBatch || mStep == 0u);
+
+    if (runTri && wantLeaf && inBlas) {
+      const int b = __ffs(tg.y) - 1;
+      tg.y &= tg.y - 1;
+      const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
+      const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+      if (DETAIL) tc.tris++;
+      // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
+      const V3 dd = mk3(r.dx, r.dy, r.dz);
+      const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
+      const V3 pv = ccross(dd, E2);
+      const float det = cdot(E1, pv);
+      const float inv = cdiv(1.0f, det);
+      const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(v0.x, v0.y, v0.z));
+      const float u = cmul(cdot(tv, pv), inv);
+      const V3 qv = ccross(tv, E1);
+      const float v = cmul(cdot(dd, qv), inv);
+      const float t = cmul(cdot(E2, qv), inv);
+      const int32_t prim = int32_t(__float_as_uint(v0.w));
+      bool ok = det != 0.0f && (u >= 0.0f && u <= 1.0f) && (v >= 0.0f && cadd(u, v) <= 1.0f) && t > tmin;
+      ok = ok && (t < hit.t || (t == hit.t && hit.inst >= 0 &&
+                                (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim))));
+      if (!ANY && ok && nonOpaque) {
+        const uint32_t g = sc.instSsbo[curInst].geometryIndex;
+        const uint32_t mi = __ldg(sc.geoms[g].matIndex + prim);
+        const float alpha = sc.mats[mi].alpha;
+        const uint32_t seed = __float_as_uint(a.seedSrc[slot].w);
+        if (alpha == 0.0f || anyHitRnd(seed, uint32_t(curInst), uint32_t(prim)) > alpha) ok = false;
+      }
+      if (ok) {
         hit.t = t;
         hit.u = u;
         hit.v = v;
         hit.inst = curInst;
         hit.prim = prim;
         hit.front = det > 0.0f ? 1u : 0u;
-        if (ANY) {
-          finished = true;
-          break;
-        }
+        if (ANY) finished = true;
       }
-    } else {
-      while (tg.y) {
-        const int b = __ffs(tg.y) - 1;
-        tg.y &= tg.y - 1;
-        const uint32_t ii = __ldg(sc.tlasInstIdx + tg.x + b);
-        const float4* ip = reinterpret_cast<const float4*>(sc.inst + ii);
-        const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-        const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
-        if (ptrs.x == 0ull) continue;
+    }
+
+    if (runInst && wantLeaf && !inBlas) {
+      const int b = __ffs(tg.y) - 1;
+      tg.y &= tg.y - 1;
+      const uint32_t ii = __ldg(sc.tlasInstIdx + tg.x + b);
+      const float4* ip = reinterpret_cast<const float4*>(sc.inst + ii);
+      const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
+      const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
+      if (ptrs.x != 0ull) {
         if (DETAIL) tc.insts++;
         // save what is left of this TLAS node, then the marker that brings us back
         if (tg.y && sp < KF_STACK) stack[sp++] = tg;
@@ -211,28 +241,10 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
         inBlas = true;
         ng = make_uint2(0u, 0x80000000u);
         tg = make_uint2(0u, 0u);
-        entered = true;
-        break;
       }
     }
-
-    if (!finished && !entered && !(ng.y & 0xff000000u)) {
-      for (;;) {
-        if (sp == 0) {
-          finished = true;
-          break;
-        }
-        const uint2 e = stack[--sp];
-        if (e.y == 0u) {  // sentinel: back to the top level
-          r = setupRay(o, d);
-          nodes = sc.tlasNodes;
-          inBlas = false;
-          continue;
-        }
-        ng = e;
-        break;
-      }
-    }
+    // a lane that has just used up its leaf group pops here, so that it can step next iteration
+    if (active && !finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
 
     if (finished) {
       if (ANY) {

@@ -25,14 +25,18 @@ struct RaySetup {
   uint32_t octinv;   // bit k set when direction k is >= 0
 };
 
+// Reciprocals feed the (conservative) box tests only, so the approximate MUFU.RCP is enough.
+KF_D float boxRcp(float x) {
+  const float eps = 1e-20f;
+  return __fdividef(1.0f, fabsf(x) > eps ? x : copysignf(eps, x));
+}
 KF_D RaySetup setupRay(V3 o, V3 d) {
   RaySetup r;
   r.ox = o.x; r.oy = o.y; r.oz = o.z;
   r.dx = d.x; r.dy = d.y; r.dz = d.z;
-  const float eps = 1e-20f;
-  r.ix = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
-  r.iy = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
-  r.iz = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+  r.ix = boxRcp(d.x);
+  r.iy = boxRcp(d.y);
+  r.iz = boxRcp(d.z);
   r.octinv = (r.ix >= 0.0f ? 1u : 0u) | (r.iy >= 0.0f ? 2u : 0u) | (r.iz >= 0.0f ? 4u : 0u);
   return r;
 }
