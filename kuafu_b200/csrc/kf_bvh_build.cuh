@@ -11,6 +11,8 @@
 // re-quantises every wide node.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "kf_common.cuh"
 
 namespace kf {
@@ -128,7 +130,8 @@ struct BlasInfo {
 };
 __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_t n,
                                  const BlasInfo* __restrict__ blas, uint32_t nBlas,
-                                 InstRec* __restrict__ recs) {
+                                 InstRec* __restrict__ recs, const float* __restrict__ primBox,
+                                 const uint32_t* __restrict__ slotOfInst, Node8* __restrict__ tlasNodes) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* m = insts[i].transform;
@@ -170,6 +173,19 @@ __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_
     rec.tris = nullptr;
   }
   recs[i] = rec;
+  // the record the traversal reads, in the top-level node array
+  InstNode in;
+#pragma unroll
+  for (int k = 0; k < 12; k++) in.inv[k] = rec.inv[k];
+  in.nodes = rec.nodes;
+  in.tris = rec.tris;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    in.box[k] = __half_as_ushort(__float2half_rd(primBox[6 * i + k]));
+    in.box[3 + k] = __half_as_ushort(__float2half_ru(primBox[6 * i + 3 + k]));
+  }
+  in.instIndex = i;
+  reinterpret_cast<InstNode*>(tlasNodes)[slotOfInst[i]] = in;
 }
 
 __global__ void __launch_bounds__(128) k_instance_box(const KfrtInstance* __restrict__ insts, uint32_t n,
@@ -497,6 +513,7 @@ struct CollapseArgs {
   int* wideBinary;            // wide node -> binary internal node it collapses
   int* wideMembers;           // 8 member codes per wide node (slot order), for refit
   uint32_t* counters;         // [0] wide nodes allocated, [1] leaf primitives allocated
+  uint32_t* slotOfInst;       // top level only: instance -> index of its InstNode in outNodes
 };
 
 KF_D int memberCount(int code, const int2* __restrict__ range) {
@@ -507,10 +524,24 @@ KF_D int memberCount(int code, const int2* __restrict__ range) {
 KF_D int memberFirst(int code, const int2* __restrict__ range) { return code < 0 ? ~code : range[code].x; }
 
 // One thread per wide node of the current level [lo, hi).
+//
+// TLAS == false (bottom level): leaves hold up to KF_LEAF_MAX triangles; meta/primBase as documented
+// at Node8.
+// TLAS == true (top level): every child is addressed like an internal child (imask = present mask,
+// meta = 0x20 | 24 + slot, children consecutive from childBase in slot order) and is either a real
+// node or an InstNode record; primBase holds the mask of the slots that are real nodes.  Instances
+// thereby take part in the octant-ordered front-to-back traversal instead of being entered in
+// storage order.
+template <bool TLAS>
 __global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
+  constexpr int LEAF_MAX = TLAS ? 1 : KF_LEAF_MAX;
   const uint32_t w = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= hi) return;
   const int b = a.wideBinary[w];
+  if (TLAS && b < 0) {  // an InstNode slot: filled by k_instance_setup, nothing to collapse
+    for (int s = 0; s < 8; s++) a.wideMembers[8 * w + s] = KF_MEMBER_EMPTY;
+    return;
+  }
   int mem[8];
   int m = 0;
   {
@@ -523,7 +554,7 @@ __global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
     int best = -1;
     float bestArea = -1.0f;
     for (int k = 0; k < m; k++) {
-      if (mem[k] >= 0 && memberCount(mem[k], a.range) > KF_LEAF_MAX) {
+      if (mem[k] >= 0 && memberCount(mem[k], a.range) > LEAF_MAX) {
         const float ar = boxArea(loadBox(a.nodeBox + 6 * mem[k]));
         if (ar > bestArea) { bestArea = ar; best = k; }
       }
@@ -573,23 +604,31 @@ __global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
   for (int s = 0; s < 8; s++) {
     if (slotMem[s] == KF_MEMBER_EMPTY) continue;
     const int cnt = memberCount(slotMem[s], a.range);
-    if (cnt > KF_LEAF_MAX) nInternal++; else nPrims += cnt;
+    if (TLAS || cnt > LEAF_MAX) nInternal++; else nPrims += cnt;
   }
   const uint32_t childBase = nInternal ? atomicAdd(a.counters + 0, nInternal) : 0u;
   const uint32_t primBase = nPrims ? atomicAdd(a.counters + 1, nPrims) : 0u;
   Node8 nd;
   nd.childBase = childBase;
   nd.primBase = primBase;
-  uint32_t imask = 0, ci = 0, po = 0;
+  uint32_t imask = 0, ci = 0, po = 0, realNodes = 0;
   for (int s = 0; s < 8; s++) {
     const int code = slotMem[s];
     a.wideMembers[8 * w + s] = code;
     if (code == KF_MEMBER_EMPTY) { nd.meta[s] = 0; continue; }
     const int cnt = memberCount(code, a.range);
-    if (cnt > KF_LEAF_MAX) {
+    if (cnt > LEAF_MAX) {
       imask |= 1u << s;
+      realNodes |= 1u << s;
       nd.meta[s] = uint8_t(0x20u | (24u + s));
       a.wideBinary[childBase + ci] = code;
+      ci++;
+    } else if (TLAS) {
+      const uint32_t prim = a.vals[memberFirst(code, a.range)];
+      imask |= 1u << s;
+      nd.meta[s] = uint8_t(0x20u | (24u + s));
+      a.wideBinary[childBase + ci] = ~int(prim);
+      a.slotOfInst[prim] = childBase + ci;
       ci++;
     } else {
       const int first = memberFirst(code, a.range);
@@ -598,6 +637,7 @@ __global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
       po += cnt;
     }
   }
+  if (TLAS) nd.primBase = realNodes;
   nd.imask = uint8_t(imask);
   quantiseNode(nd, nb, slotBox, used);
   a.outNodes[w] = nd;
@@ -624,12 +664,35 @@ __global__ void k_single_leaf_root(int n, const float* __restrict__ primBox, Nod
   storeBox(rootBox, nb);
 }
 
-// Refit: re-quantise every wide node from its members' freshly recomputed boxes.
-__global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers,
+// Top-level root for a single instance: node 0 with one child, the InstNode at index 1.
+__global__ void k_single_instance_root(const float* __restrict__ primBox, Node8* outNodes, int* wideBinary,
+                                       int* wideMembers, uint32_t* slotOfInst, float* rootBox) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const Box6 nb = loadBox(primBox);
+  Node8 nd;
+  nd.childBase = 1;
+  nd.primBase = 0;  // no real-node children
+  nd.imask = 1;
+  Box6 slotBox[8];
+  for (int s = 0; s < 8; s++) { nd.meta[s] = 0; wideMembers[s] = KF_MEMBER_EMPTY; wideMembers[8 + s] = KF_MEMBER_EMPTY; }
+  nd.meta[0] = uint8_t(0x20u | 24u);
+  slotBox[0] = nb;
+  quantiseNode(nd, nb, slotBox, 1u);
+  outNodes[0] = nd;
+  wideBinary[0] = 0;
+  wideBinary[1] = ~0;
+  slotOfInst[0] = 1;
+  storeBox(rootBox, nb);
+}
+
+// Refit: re-quantise every wide node from its members' freshly recomputed boxes.  wideBinary < 0
+// marks the InstNode slots of a top-level array, which k_instance_setup rewrites instead.
+__global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers, const int* __restrict__ wideBinary,
                              const float* __restrict__ nodeBox, const float* __restrict__ primBox,
                              const uint32_t* __restrict__ vals, Node8* nodes, int singleLeafN) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nWide) return;
+  if (wideBinary && wideBinary[w] < 0) return;
   Box6 nb;
   boxReset(nb);
   Box6 slotBox[8];

@@ -125,13 +125,25 @@ struct __align__(16) Tri48 {
 };
 static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 
-// Instance record read when a ray enters a bottom-level structure, 64 bytes = 4 x 16 B loads.
+// Per-instance shading record (world->object for the normal transform), indexed by instance.
 struct __align__(16) InstRec {
   float inv[12];          // world->object, 3 rows x 4 columns
   const Node8* nodes;     // BLAS nodes (root = nodes[0]); NULL when the geometry is hidden/empty
   const Tri48* tris;      // BLAS triangles in leaf order; bit 0 set == non-opaque geometry
 };
 static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
+
+// Instance record as it sits in the top-level node array (same 80-byte stride as a Node8, addressed
+// like an internal child): what a ray needs to enter a bottom-level structure, 5 x 16 B loads.
+struct __align__(16) InstNode {
+  float inv[12];       // world->object, 3 rows x 4 columns
+  const Node8* nodes;  // BLAS nodes; NULL when the geometry is hidden/empty
+  const Tri48* tris;   // BLAS triangles in leaf order; bit 0 set == non-opaque geometry
+  uint16_t box[6];     // world box as fp16 bits, rounded outward: lo.xyz, hi.xyz (re-test against the
+                       // current closest hit before the ray is transformed)
+  uint32_t instIndex;  // instance index (gl_InstanceID)
+};
+static_assert(sizeof(InstNode) == 80, "InstNode must be 80 bytes");
 
 // Per-geometry shading tables (fetched only at shading time).
 struct GeomRec {
@@ -148,8 +160,7 @@ struct TexRec {
 };
 
 struct SceneDev {
-  const Node8* tlasNodes;
-  const uint32_t* tlasInstIdx;  // leaf order -> instance index
+  const Node8* tlasNodes;  // top level: Node8 and InstNode records in one array (kf_bvh_build.cuh)
   const InstRec* inst;
   const KfrtInstance* instSsbo;
   const GeomRec* geoms;

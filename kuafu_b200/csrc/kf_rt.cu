@@ -84,7 +84,7 @@ struct BuildState {
   DevBuf<float> primBox;
   DevBuf<int> sceneBox;
   DevBuf<uint64_t> keysA, keysB;
-  DevBuf<uint32_t> valsA, valsB, hist, flags, outPrim, counters;
+  DevBuf<uint32_t> valsA, valsB, hist, flags, outPrim, counters, slotOfInst;
   DevBuf<int2> children, range;
   DevBuf<int> parent, wideBinary, wideMembers;
   DevBuf<float> nodeBox;
@@ -94,7 +94,7 @@ struct BuildState {
     primBox.release(); sceneBox.release(); keysA.release(); keysB.release(); valsA.release();
     valsB.release(); hist.release(); flags.release(); outPrim.release(); counters.release();
     children.release(); range.release(); parent.release(); wideBinary.release();
-    wideMembers.release(); nodeBox.release(); outNodes.release();
+    wideMembers.release(); nodeBox.release(); outNodes.release(); slotOfInst.release();
   }
 };
 
@@ -127,7 +127,6 @@ struct KfrtContext {
   std::vector<KfrtInstance> instHost;
   DevBuf<KfrtInstance> instDev;
   DevBuf<InstRec> instRec;
-  DevBuf<uint32_t> tlasInstIdx;
   DevBuf<Node8> tlasNodes;
   uint32_t nTlasNodes = 0;
   bool blasBuilt = false, tlasBuilt = false;
@@ -147,9 +146,7 @@ struct KfrtContext {
   uint64_t launches = 0;
   // wavefront scheduler state
   int numSMs = 148;
-  int scheduler = 1;  // 1 wavefront (default), 0 megakernel (KFRT_SCHEDULER=mega; round-1 baseline kept for A/B)
   size_t batchSlotTarget = size_t(16) << 20;
-  int triBatch = KF_TRI_BATCH, instBatch = KF_INST_BATCH;
   size_t wfSlots = 0;
   bool wfMulti = false;
   DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
@@ -204,15 +201,26 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
 
 // Builds the wide BVH over st.primBox[0..n) (already filled, with st.sceneBox).  On return
 // st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
-static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n) {
+// tlas: top-level layout -- every instance becomes an InstNode slot inside outNodes (st.slotOfInst),
+// so the array holds up to n real nodes plus n instance slots.
+static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
   st.n = n;
-  KF_CUDA(ctx, st.outNodes.ensure(std::max<uint32_t>(n, 1)));
+  const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
+  KF_CUDA(ctx, st.outNodes.ensure(maxNodes));
   KF_CUDA(ctx, st.outPrim.ensure(n));
-  KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * std::max<uint32_t>(n, 1)));
-  KF_CUDA(ctx, st.wideBinary.ensure(std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * maxNodes));
+  KF_CUDA(ctx, st.wideBinary.ensure(maxNodes));
   KF_CUDA(ctx, st.counters.ensure(2));
   KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
-  if (n <= KF_LEAF_MAX) {
+  if (tlas) KF_CUDA(ctx, st.slotOfInst.ensure(std::max<uint32_t>(n, 1)));
+  if (tlas && n == 1) {
+    k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, st.outNodes.p, st.wideBinary.p,
+                                                      st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
+    st.nWide = 2;
+    KF_CUDA(ctx, cudaGetLastError());
+    return KFRT_OK;
+  }
+  if (!tlas && n <= KF_LEAF_MAX) {
     k_single_leaf_root<<<1, 32, 0, ctx->stream>>>(int(n), st.primBox.p, st.outNodes.p, st.outPrim.p,
                                                   st.wideMembers.p, st.nodeBox.p);
     st.nWide = 1;
@@ -252,15 +260,17 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n) {
   a.wideBinary = st.wideBinary.p;
   a.wideMembers = st.wideMembers.p;
   a.counters = st.counters.p;
+  a.slotOfInst = tlas ? st.slotOfInst.p : nullptr;
   uint32_t lo = 0, hi = 1;
   while (lo < hi) {
-    k_collapse_level<<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
+    if (tlas) k_collapse_level<true><<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
+    else k_collapse_level<false><<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
     uint32_t cnt = 0;
     KF_CUDA(ctx, cudaMemcpyAsync(&cnt, st.counters.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     lo = hi;
     hi = cnt;
-    if (hi > n) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
+    if (hi > maxNodes) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
   }
   st.nWide = hi;
   KF_CUDA(ctx, cudaGetLastError());
@@ -288,7 +298,7 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   KF_CUDA(ctx, st.sceneBox.ensure(6));
   k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
   k_tri_boxes<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, nTris, st.primBox.p, st.sceneBox.p);
-  int rc = buildWideBvh(ctx, st, nTris);
+  int rc = buildWideBvh(ctx, st, nTris, false);
   if (rc) return rc;
   KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.nodes), sizeof(Node8) * st.nWide));
   KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris));
@@ -365,135 +375,6 @@ struct RenderArgs {
   float* depth;
   unsigned long long* counters;  // [0] paths [1] ext [2] shadow [3] hits [4] nodes [5] tris [6] insts [7] tex
 };
-
-KF_D unsigned long long warpSum(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// One thread per pixel: the whole of PathTrace.rgen:19-141 with traversal and shading inlined.
-// (Round-1 baseline scheduler; the wavefront scheduler reuses the same device functions.)
-template <bool DETAIL>
-__global__ void __launch_bounds__(64) k_render_mega(RenderArgs a) {
-  const uint32_t x = blockIdx.x * 8 + (threadIdx.x & 7);
-  const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 3);
-  const uint32_t c = blockIdx.z;
-  unsigned long long nExt = 0, nSh = 0, nHit = 0, nTex = 0;
-  TravCounters tc{0, 0, 0};
-  unsigned long long nNodes = 0, nTris = 0, nInsts = 0;
-  if (x < a.w && y < a.h) {
-    const KfrtCamera* cam = a.cams + c;
-    const KfrtPushConstants& pc = a.pc;
-    const uint32_t mapping = y * a.w + x;
-    uint32_t seed = tea(mapping, a.clockBase);
-    for (uint32_t k = 0; k < 2 * a.s0; k++) lcg(seed);
-    V3 colors = mk3(0.0f), albedoOut = mk3(0.0f), normalOut = mk3(0.0f);
-    int32_t hitInst = -1, hitPrim = -1;
-    float hitT = 0.0f, hitDepth = 0.0f;
-    for (uint32_t i = a.s0; i < a.s1; ++i) {
-      uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
-      V3 ro, rd;
-      cameraRay(cam, x, y, a.w, a.h, seed, raySeed, ro, rd);
-      V3 weight = mk3(1.0f), color = mk3(0.0f);
-      V3 rayWeight = mk3(0.0f);  // ray.weight persists across bounces (stale on miss / emissive)
-      for (uint32_t depth = 0; depth <= pc.maxPathDepth; ++depth) {
-        Hit hit;
-        nExt++;
-        const bool found = traverse<false, DETAIL>(a.sc, ro, rd, 0.001f, 10000.0f, raySeed, hit, tc);
-        if (i == 0 && depth == 0 && found) {
-          hitInst = hit.inst;
-          hitPrim = hit.prim;
-          hitT = hit.t;
-          // view-space depth: -(view * P).z with P = o + d * t (contract arithmetic)
-          const float Px = cadd(ro.x, cmul(rd.x, hit.t)), Py = cadd(ro.y, cmul(rd.y, hit.t)),
-                      Pz = cadd(ro.z, cmul(rd.z, hit.t));
-          const float* vm = cam->view;
-          hitDepth = -cadd(cadd(cadd(cmul(vm[2], Px), cmul(vm[6], Py)), cmul(vm[10], Pz)), vm[14]);
-        }
-        V3 emission = mk3(0.0f), shadowColor = mk3(0.0f), albedo = mk3(0.0f), N = mk3(0.0f);
-        bool pathEnds = false;
-        uint32_t tex = 0;
-        if (found) {
-          nHit++;
-          Surface sf;
-          V3 L, w;
-          if (shadeSurface(a.sc, hit, ro, rd, raySeed, sf, L, w, albedo, emission, tex)) {
-            // next-event estimation, lights in reference order (rchit:457-460)
-            int k = 0;
-            V3 Ls, le;
-            float maxDist;
-            while (nextLight(a.sc, sf, raySeed, k, Ls, maxDist, le, tex)) {
-              Hit sh;
-              nSh++;
-              const bool occluded = traverse<true, DETAIL>(a.sc, sf.worldPos, Ls, 0.001f, maxDist, 0u, sh, tc);
-              if (!occluded) shadowColor += calcDirect(sf, Ls, le, raySeed);
-              k++;
-            }
-            ro = sf.worldPos;
-            rd = L;
-            rayWeight = w;
-            N = sf.N;
-          } else {
-            pathEnds = true;  // emissive surface: ray.depth = maxPathDepth + 1 (rchit:330-334)
-          }
-        } else {
-          emission = shadeMiss(a.sc, pc, rd, tex);
-          pathEnds = true;  // rmiss:30
-        }
-        nTex += tex;
-        color += emission * weight;
-        weight *= rayWeight;
-        color += shadowColor * weight;
-        if (i == 0 && depth == 0 && !pathEnds) {  // rgen:114-117 (ray.depth is still 0 only for surfaces)
-          albedoOut = albedo;
-          normalOut = N;
-        }
-        if (allEq(weight, mk3(0.0f))) break;
-        // Russian roulette (rgen:124-138); after a miss/emissive hit ray.depth = maxPathDepth + 1,
-        // the draw below is then unobservable (the stream is re-seeded per sample), so skip it.
-        if (pathEnds) break;
-        if (pc.russianRoulette && depth >= pc.russianRouletteMinBounces) {
-          const float p = fmaxf(weight.x, fmaxf(weight.y, weight.z));
-          const float r = rnd(raySeed);
-          if (r > p) break;
-          weight *= 1.0f / p;
-        }
-      }
-      colors += color;
-    }
-    const size_t pi = (size_t(c) * a.h + y) * a.w + x;
-    a.sum[pi] = make_float4(colors.x, colors.y, colors.z, float(a.s1 - a.s0));
-    if (a.s0 == 0) {
-      a.albedo[pi] = make_float4(albedoOut.x, albedoOut.y, albedoOut.z, 1.0f);
-      a.normal[pi] = make_float4(normalOut.x, normalOut.y, normalOut.z, 1.0f);
-      a.hitIds[pi] = make_int2(hitInst, hitPrim);
-      a.hitT[pi] = hitT;
-      a.depth[pi] = hitDepth;
-    }
-    if (DETAIL) { nNodes = tc.nodes; nTris = tc.tris; nInsts = tc.insts; }
-  }
-  nExt = warpSum(nExt);
-  nSh = warpSum(nSh);
-  nHit = warpSum(nHit);
-  if (DETAIL) {
-    nNodes = warpSum(nNodes);
-    nTris = warpSum(nTris);
-    nInsts = warpSum(nInsts);
-    nTex = warpSum(nTex);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(a.counters + 1, nExt);
-    atomicAdd(a.counters + 2, nSh);
-    atomicAdd(a.counters + 3, nHit);
-    if (DETAIL) {
-      atomicAdd(a.counters + 4, nNodes);
-      atomicAdd(a.counters + 5, nTris);
-      atomicAdd(a.counters + 6, nInsts);
-      atomicAdd(a.counters + 7, nTex);
-    }
-  }
-}
 
 // Accumulate + encode (reference PathTrace.rgen:143-163, PostProcessing.frag:11-18 into a
 // B8G8R8A8Srgb attachment).  The 8-bit sRGB code is found by binary search over the 255 linear
@@ -574,9 +455,6 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
   }
   ctx->stream = ctx->ownStream;
   ctx->numSMs = prop.multiProcessorCount;
-  if (const char* e = std::getenv("KFRT_SCHEDULER")) ctx->scheduler = std::strcmp(e, "mega") == 0 ? 0 : 1;
-  if (const char* e = std::getenv("KFRT_TRI_BATCH")) ctx->triBatch = std::atoi(e);
-  if (const char* e = std::getenv("KFRT_INST_BATCH")) ctx->instBatch = std::atoi(e);
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
     if (v > 0) ctx->batchSlotTarget = size_t(v);
@@ -619,7 +497,7 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->geomTable.release(); ctx->blasInfo.release(); ctx->mats.release(); ctx->texTable.release();
   ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
-  ctx->instRec.release(); ctx->tlasInstIdx.release(); ctx->tlasNodes.release();
+  ctx->instRec.release(); ctx->tlasNodes.release();
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
   ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
   ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
@@ -806,7 +684,8 @@ int kfrtSetInstances(KfrtContext* ctx, const KfrtInstance* instances, uint32_t n
   return KFRT_OK;
 }
 
-static int instanceSetup(KfrtContext* ctx, bool withSceneBox) {
+// World boxes of all instances (input of the top-level build / refit).
+static int instanceBoxes(KfrtContext* ctx, bool withSceneBox) {
   const uint32_t n = uint32_t(ctx->instHost.size());
   BuildState& st = ctx->tlasBuild;
   KF_CUDA(ctx, ctx->instDev.ensure(std::max<uint32_t>(n, 1)));
@@ -817,10 +696,20 @@ static int instanceSetup(KfrtContext* ctx, bool withSceneBox) {
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->instDev.p, ctx->instHost.data(), sizeof(KfrtInstance) * n,
                                cudaMemcpyHostToDevice, ctx->stream));
   if (withSceneBox) k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
-  k_instance_setup<<<gridFor(n, 128), 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p,
-                                                             uint32_t(ctx->geoms.size()), ctx->instRec.p);
   k_instance_box<<<n, 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p, uint32_t(ctx->geoms.size()),
                                              st.primBox.p, withSceneBox ? st.sceneBox.p : nullptr);
+  KF_CUDA(ctx, cudaGetLastError());
+  return KFRT_OK;
+}
+
+// Inverse transforms: the per-instance shading records and the InstNode slots of the top-level array.
+static int instanceRecords(KfrtContext* ctx) {
+  const uint32_t n = uint32_t(ctx->instHost.size());
+  BuildState& st = ctx->tlasBuild;
+  if (n == 0) return KFRT_OK;
+  k_instance_setup<<<gridFor(n, 128), 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p,
+                                                             uint32_t(ctx->geoms.size()), ctx->instRec.p,
+                                                             st.primBox.p, st.slotOfInst.p, ctx->tlasNodes.p);
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -836,7 +725,7 @@ int kfrtBuildTlas(KfrtContext* ctx) {
     if (rc) return rc;
   }
   const uint32_t n = uint32_t(ctx->instHost.size());
-  int rc = instanceSetup(ctx, true);
+  int rc = instanceBoxes(ctx, true);
   if (rc) return rc;
   if (n == 0) {
     ctx->nTlasNodes = 0;
@@ -844,12 +733,12 @@ int kfrtBuildTlas(KfrtContext* ctx) {
     return KFRT_OK;
   }
   BuildState& st = ctx->tlasBuild;
-  rc = buildWideBvh(ctx, st, n);
+  rc = buildWideBvh(ctx, st, n, true);
   if (rc) return rc;
   KF_CUDA(ctx, ctx->tlasNodes.ensure(st.nWide));
-  KF_CUDA(ctx, ctx->tlasInstIdx.ensure(n));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasNodes.p, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasInstIdx.p, st.outPrim.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  rc = instanceRecords(ctx);
+  if (rc) return rc;
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->nTlasNodes = st.nWide;
   ctx->tlasBuilt = true;
@@ -864,19 +753,22 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   if (n == 0) return KFRT_OK;
   if (!transforms) KF_FAIL(ctx, KFRT_ERR_INVALID, "null transforms");
   for (uint32_t i = 0; i < n; i++) std::memcpy(ctx->instHost[i].transform, transforms + 16 * i, 64);
-  int rc = instanceSetup(ctx, false);
+  int rc = instanceBoxes(ctx, false);
   if (rc) return rc;
   BuildState& st = ctx->tlasBuild;
-  if (n > KF_LEAF_MAX) {
+  if (n > 1) {
     KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
     k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
                                                             st.sortedVals, st.nodeBox.p, st.flags.p);
-    k_requantise<<<gridFor(st.nWide, 128), 128, 0, ctx->stream>>>(st.nWide, st.wideMembers.p, st.nodeBox.p,
-                                                                  st.primBox.p, st.sortedVals, ctx->tlasNodes.p, 0);
+    k_requantise<<<gridFor(st.nWide, 128), 128, 0, ctx->stream>>>(st.nWide, st.wideMembers.p, st.wideBinary.p,
+                                                                  st.nodeBox.p, st.primBox.p, st.sortedVals,
+                                                                  ctx->tlasNodes.p, 0);
   } else {
-    k_requantise<<<1, 32, 0, ctx->stream>>>(1u, st.wideMembers.p, st.nodeBox.p, st.primBox.p, st.sortedVals,
-                                            ctx->tlasNodes.p, int(n));
+    k_requantise<<<1, 32, 0, ctx->stream>>>(1u, st.wideMembers.p, nullptr, st.nodeBox.p, st.primBox.p,
+                                            st.sortedVals, ctx->tlasNodes.p, 1);
   }
+  rc = instanceRecords(ctx);
+  if (rc) return rc;
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -897,7 +789,7 @@ int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   out->tlasNodeCount = ctx->nTlasNodes;
   out->nodeBytes = sizeof(Node8);
   out->triangleBytes = sizeof(Tri48);
-  out->instanceBytes = sizeof(InstRec);
+  out->instanceBytes = sizeof(InstNode);
   return KFRT_OK;
 }
 
@@ -1020,8 +912,6 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.counters = a.counters;
       te.rayCounter = 1;
       te.detailBase = 4;
-      te.triBatch = ctx->triBatch;
-      te.instBatch = ctx->instBatch;
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
       else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
       switch (variant) {
@@ -1091,7 +981,6 @@ static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t 
 static SceneDev sceneDev(KfrtContext* ctx) {
   SceneDev sc{};
   sc.tlasNodes = ctx->nTlasNodes ? ctx->tlasNodes.p : nullptr;
-  sc.tlasInstIdx = ctx->tlasInstIdx.p;
   sc.inst = ctx->instRec.p;
   sc.instSsbo = ctx->instDev.p;
   sc.geoms = ctx->geomTable.p;
@@ -1143,18 +1032,8 @@ int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, u
   a.hitT = ctx->hitT.p;
   a.depth = ctx->depth.p;
   a.counters = ctx->counters.p;
-  if (ctx->scheduler == 0) {
-    const dim3 grid((width + 7) / 8, (height + 7) / 8, nCameras);
-    if (ctx->detail)
-      k_render_mega<true><<<grid, 64, 0, ctx->stream>>>(a);
-    else
-      k_render_mega<false><<<grid, 64, 0, ctx->stream>>>(a);
-    KF_CUDA(ctx, cudaGetLastError());
-    ctx->launches = 1;
-  } else {
-    rc = renderWavefront(ctx, a);
-    if (rc) return rc;
-  }
+  rc = renderWavefront(ctx, a);
+  if (rc) return rc;
   ctx->lastPc = *pc;
   ctx->rendered = true;
   ctx->lastCounters = KfrtCounters{};

@@ -7,18 +7,21 @@
 // ray from the stage queue (one warp-aggregated atomic per refill).  With incoherent bounce rays the
 // per-ray traversal length varies by an order of magnitude, so this is what keeps lanes busy.
 //
-// Every lane iteration is one traversal step:
-//   [node]      pop the nearest pending child of the current node group, fetch its 80-byte node
-//               (5 x 16 B loads), slab-test its 8 quantised child boxes
-//   [triangle]  (bottom level) Moller-Trumbore on the leaf triangles of the current group
-//   [instance]  (top level) enter the next instance of the current leaf group: 64-byte record,
-//               world -> object ray transform
-//   [pop]       next group from the stack; a sentinel entry returns from the bottom level
+// Every loop iteration runs the phases below warp-wide, each lane taking part in those that match
+// its state (so that lanes doing the same kind of work do it in the same instructions):
+//   [instance]  (top level) the nearest pending child is an InstNode: re-test its world box against
+//               the current closest hit, then world -> object ray transform and enter its BLAS root
+//   [node]      take the nearest pending child node, fetch its 80 bytes (5 x 16 B loads), slab-test
+//               its 8 quantised child boxes
+//   [pop]       next group from the stack; a sentinel entry returns to the top level
+//   [triangle]  (bottom level) Moller-Trumbore on one leaf triangle of the current group
 //
 // Results do not depend on traversal order: boxes are conservative and equal-t ties resolve to the
 // lowest (instance, primitive) pair (oracle deviation D3), so hit buffers stay bit-exact with the
 // CPU oracle whatever the scheduling.
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "kf_common.cuh"
 #include "kf_traverse.cuh"
@@ -26,12 +29,6 @@
 namespace kf {
 
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
-#ifndef KF_TRI_BATCH
-#define KF_TRI_BATCH 1   // run the triangle phase once this many lanes wait for it
-#endif
-#ifndef KF_INST_BATCH
-#define KF_INST_BATCH 1   // same for the instance-entry phase
-#endif
 
 struct TraceArgs {
   SceneDev sc;
@@ -49,7 +46,6 @@ struct TraceArgs {
   unsigned long long* counters;
   int rayCounter;            // counters[] index that receives the number of rays of this stage
   int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
-  int triBatch, instBatch;   // lanes that must wait for a leaf phase before the warp runs it
 };
 
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
@@ -84,8 +80,8 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
   uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
 
   bool finished = false;
-  // Next group from the lane's stack: a node group goes to ng, a primitive group to tg; a sentinel
-  // (x, 0) returns from the bottom level; an empty stack ends the ray.
+  // Next group from the lane's stack: a node group goes to ng, a triangle group to tg; a sentinel
+  // (x, 0) returns to the top level; an empty stack ends the ray.
   auto popGroup = [&]() {
     for (;;) {
       if (sp == 0) {
@@ -136,7 +132,8 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
             nonOpaque = false;
             curInst = -1;
             sp = 0;
-            ng = make_uint2(0u, sc.tlasNodes ? 0x80000000u : 0u);
+            // the root is "child 7 ^ octinv of a virtual parent": a real node, present mask empty
+            ng = make_uint2(0u, sc.tlasNodes ? (0x80000000u | 0x0000ff00u) : 0u);
             tg = make_uint2(0u, 0u);
             active = true;
           }
@@ -145,35 +142,79 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
       }
       if (exhausted && __ballot_sync(0xffffffffu, active) == 0u) break;
     }
-    // ---- node phase: lanes without pending leaf work take one node step ---------------------
     finished = false;
+
+    // ---- instance phase (top level): the nearest pending child is an InstNode ------------------
+    if (active && !inBlas && (ng.y & 0xff000000u)) {
+      const uint32_t hits = ng.y;
+      const int p = 31 - __clz(hits);
+      const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;
+      if (!((hits >> (8 + cslot)) & 1u)) {
+        ng.y &= ~(1u << p);
+        const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
+        const uint4* ip = reinterpret_cast<const uint4*>(nodes + ng.x + rel);
+        const uint4 w4 = __ldg(ip + 4);
+        if (DETAIL) tc.insts++;
+        // re-test the instance's own world box against what is now the closest hit
+        const float2 lxy = __half22float2(*reinterpret_cast<const __half2*>(&w4.x));
+        const float2 lzhx = __half22float2(*reinterpret_cast<const __half2*>(&w4.y));
+        const float2 hyz = __half22float2(*reinterpret_cast<const __half2*>(&w4.z));
+        const float ax0 = (lxy.x - r.ox) * r.ix, ax1 = (lzhx.y - r.ox) * r.ix;
+        const float ay0 = (lxy.y - r.oy) * r.iy, ay1 = (hyz.x - r.oy) * r.iy;
+        const float az0 = (lzhx.x - r.oz) * r.iz, az1 = (hyz.y - r.oz) * r.iz;
+        const float t0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
+        const float t1 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), hit.t));
+        const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
+        if (t0 <= t1 && ptrs.x != 0ull) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(ip) + 0);
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
+          const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);
+          // what is left of this top-level node, then the marker that brings us back
+          if ((ng.y & 0xff000000u) && sp < KF_STACK) stack[sp++] = ng;
+          if (sp < KF_STACK) stack[sp++] = make_uint2(0xffffffffu, 0u);
+          // world -> object (contract arithmetic, oracle traceInstance())
+          V3 oo, od;
+          oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
+          oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
+          oo.z = cadd(cdot3(r2.x, r2.y, r2.z, o.x, o.y, o.z), r2.w);
+          od.x = cdot3(r0.x, r0.y, r0.z, d.x, d.y, d.z);
+          od.y = cdot3(r1.x, r1.y, r1.z, d.x, d.y, d.z);
+          od.z = cdot3(r2.x, r2.y, r2.z, d.x, d.y, d.z);
+          r = setupRay(oo, od);
+          nodes = reinterpret_cast<const Node8*>(ptrs.x);
+          nonOpaque = (ptrs.y & 1ull) != 0;
+          tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
+          curInst = int32_t(w4.w);
+          inBlas = true;
+          ng = make_uint2(0u, 0x80000000u);  // bottom-level root; steps in the node phase below
+        }
+      }
+    }
+
+    // ---- node phase: lanes without pending triangles take one node step -------------------------
     if (active && tg.y == 0u && (ng.y & 0xff000000u)) {
       const uint32_t hits = ng.y;
       const int p = 31 - __clz(hits);
-      ng.y &= ~(1u << p);
-      if (ng.y & 0xff000000u) {
-        if (sp < KF_STACK) stack[sp++] = ng;
-      }
       const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;
-      const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
-      uint32_t childBase, primBase, imask;
-      const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);
-      if (DETAIL) tc.nodes++;
-      ng = make_uint2(childBase, (hm & 0xff000000u) | imask);
-      tg = make_uint2(primBase, hm & 0x00ffffffu);
+      if (inBlas || ((hits >> (8 + cslot)) & 1u)) {
+        ng.y &= ~(1u << p);
+        if (ng.y & 0xff000000u) {
+          if (sp < KF_STACK) stack[sp++] = ng;
+        }
+        const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
+        uint32_t childBase, primBase, imask;
+        const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);
+        if (DETAIL) tc.nodes++;
+        // top level: imask = present children, primBase = which of them are real nodes
+        ng = make_uint2(childBase, (hm & 0xff000000u) | imask | (inBlas ? 0u : (primBase & 0xffu) << 8));
+        tg = make_uint2(primBase, inBlas ? (hm & 0x00ffffffu) : 0u);
+      }
     }
     // ---- pop: lanes with nothing in hand take the next group from their stack ------------------
     if (active && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
 
-    // ---- leaf phases run warp-wide, once enough lanes wait for them (or nobody can step) ------
-    const bool wantLeaf = active && !finished && tg.y != 0u;
-    const uint32_t mTri = __ballot_sync(0xffffffffu, wantLeaf && inBlas);
-    const uint32_t mInst = __ballot_sync(0xffffffffu, wantLeaf && !inBlas);
-    const uint32_t mStep = __ballot_sync(0xffffffffu, active && !finished && tg.y == 0u);
-    const bool runTri = mTri != 0u && (__popc(mTri) >= a.triBatch || mStep == 0u);
-    const bool runInst = mInst != 0u && (__popc(mInst) >= a.instBatch || mStep == 0u);
-
-    if (runTri && wantLeaf && inBlas) {
+    // ---- triangle phase (bottom level): one leaf triangle per lane -------------------------------
+    if (active && !finished && tg.y != 0u) {
       const int b = __ffs(tg.y) - 1;
       tg.y &= tg.y - 1;
       const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
@@ -210,41 +251,9 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
         hit.front = det > 0.0f ? 1u : 0u;
         if (ANY) finished = true;
       }
+      // a lane that has just used up its leaf group pops here, so that it can step next iteration
+      if (!finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
     }
-
-    if (runInst && wantLeaf && !inBlas) {
-      const int b = __ffs(tg.y) - 1;
-      tg.y &= tg.y - 1;
-      const uint32_t ii = __ldg(sc.tlasInstIdx + tg.x + b);
-      const float4* ip = reinterpret_cast<const float4*>(sc.inst + ii);
-      const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-      const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
-      if (ptrs.x != 0ull) {
-        if (DETAIL) tc.insts++;
-        // save what is left of this TLAS node, then the marker that brings us back
-        if (tg.y && sp < KF_STACK) stack[sp++] = tg;
-        if ((ng.y & 0xff000000u) && sp < KF_STACK) stack[sp++] = ng;
-        if (sp < KF_STACK) stack[sp++] = make_uint2(0xffffffffu, 0u);
-        // world -> object (contract arithmetic, oracle traceInstance())
-        V3 oo, od;
-        oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
-        oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
-        oo.z = cadd(cdot3(r2.x, r2.y, r2.z, o.x, o.y, o.z), r2.w);
-        od.x = cdot3(r0.x, r0.y, r0.z, d.x, d.y, d.z);
-        od.y = cdot3(r1.x, r1.y, r1.z, d.x, d.y, d.z);
-        od.z = cdot3(r2.x, r2.y, r2.z, d.x, d.y, d.z);
-        r = setupRay(oo, od);
-        nodes = reinterpret_cast<const Node8*>(ptrs.x);
-        nonOpaque = (ptrs.y & 1ull) != 0;
-        tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
-        curInst = int32_t(ii);
-        inBlas = true;
-        ng = make_uint2(0u, 0x80000000u);
-        tg = make_uint2(0u, 0u);
-      }
-    }
-    // a lane that has just used up its leaf group pops here, so that it can step next iteration
-    if (active && !finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
 
     if (finished) {
       if (ANY) {

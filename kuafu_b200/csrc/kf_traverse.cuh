@@ -1,11 +1,13 @@
-// kf_traverse.cuh -- two-level traversal of the compressed 8-wide BVH (replaces traceRayEXT and the
-// driver/RT-core traversal behind it: reference PathTrace.rgen:97-107, PathTrace.rchit:186-197).
+// kf_traverse.cuh -- building blocks of the two-level traversal of the compressed 8-wide BVH (ray
+// setup, the 8-box slab test of one node); the traversal loop itself is the persistent kernel in
+// kf_trace.cuh.
 //
-// One thread walks one ray.  State is a small stack of 8-byte "groups":
-//   node group      (childBase, hits<<24 | imask)   -- internal children still to visit, in
-//                                                      octant priority order (highest bit first)
-//   primitive group (primBase, 24-bit mask)         -- triangles (BLAS) or instance entries (TLAS)
-//   sentinel        (x, 0)                          -- marks the return from a BLAS to the TLAS
+// Traversal state is a small stack of 8-byte "groups":
+//   node group      (childBase, hits<<24 | kind<<8 | mask) -- children still to visit, in octant
+//                    priority order (highest bit first); mask = internal children (bottom level) or
+//                    present children (top level, where kind marks the real nodes among them)
+//   primitive group (primBase, 24-bit mask)                -- leaf triangles (bottom level)
+//   sentinel        (x, 0)                                 -- marks the return to the top level
 #pragma once
 
 #include "kf_common.cuh"
@@ -108,145 +110,6 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
 KF_D float anyHitRnd(uint32_t seed, uint32_t inst, uint32_t prim) {
   uint32_t h = tea(seed ^ (prim * 0x9e3779b9u), inst);
   return float(h & 0x00FFFFFFu) * (1.0f / 16777216.0f);
-}
-
-// Closest hit (ANY == false; any-hit alpha test on non-opaque geometry) or first hit (ANY == true;
-// gl_RayFlagsTerminateOnFirstHit | Opaque | SkipClosestHitShader) in the open interval (tmin, tmax).
-template <bool ANY, bool DETAIL>
-KF_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tmin, float tmax, uint32_t seed, Hit& hit,
-                   TravCounters& tc) {
-  uint2 stack[KF_STACK];
-  int sp = 0;
-  hit.t = tmax;
-  hit.u = hit.v = 0.0f;
-  hit.inst = -1;
-  hit.prim = -1;
-  hit.front = 0;
-  if (sc.tlasNodes == nullptr) return false;
-
-  RaySetup r = setupRay(o, d);
-  const Node8* nodes = sc.tlasNodes;
-  const Tri48* tris = nullptr;
-  bool inBlas = false, nonOpaque = false;
-  int32_t curInst = -1;
-  uint2 ng = make_uint2(0u, 0x80000000u);
-  uint2 tg = make_uint2(0u, 0u);
-
-  for (;;) {
-    if (ng.y & 0xff000000u) {
-      const uint32_t hits = ng.y;
-      const int p = 31 - __clz(hits);
-      ng.y &= ~(1u << p);
-      if (ng.y & 0xff000000u) {
-        if (sp < KF_STACK) stack[sp++] = ng;
-      }
-      const uint32_t slot = uint32_t(p - 24) ^ r.octinv;
-      const uint32_t rel = __popc(hits & 0xffu & ((1u << slot) - 1u));
-      uint32_t childBase, primBase, imask;
-      const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);
-      if (DETAIL) tc.nodes++;
-      ng = make_uint2(childBase, (hm & 0xff000000u) | imask);
-      tg = make_uint2(primBase, hm & 0x00ffffffu);
-    } else {
-      tg = ng;  // a popped primitive group (or nothing)
-      ng = make_uint2(0u, 0u);
-    }
-
-    if (inBlas) {
-      while (tg.y) {
-        const int b = __ffs(tg.y) - 1;
-        tg.y &= tg.y - 1;
-        const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
-        const float4 a = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-        if (DETAIL) tc.tris++;
-        // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
-        const V3 dd = mk3(r.dx, r.dy, r.dz);
-        const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
-        const V3 pv = ccross(dd, E2);
-        const float det = cdot(E1, pv);
-        if (det == 0.0f) continue;
-        const float inv = cdiv(1.0f, det);
-        const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(a.x, a.y, a.z));
-        const float u = cmul(cdot(tv, pv), inv);
-        if (!(u >= 0.0f && u <= 1.0f)) continue;
-        const V3 qv = ccross(tv, E1);
-        const float v = cmul(cdot(dd, qv), inv);
-        if (!(v >= 0.0f && cadd(u, v) <= 1.0f)) continue;
-        const float t = cmul(cdot(E2, qv), inv);
-        if (!(t > tmin)) continue;
-        const int32_t prim = int32_t(__float_as_uint(a.w));
-        const bool closer =
-            t < hit.t || (t == hit.t && hit.inst >= 0 &&
-                          (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim)));
-        if (!closer) continue;
-        if (!ANY && nonOpaque) {
-          const uint32_t g = sc.instSsbo[curInst].geometryIndex;
-          const uint32_t mi = __ldg(sc.geoms[g].matIndex + prim);
-          const float alpha = sc.mats[mi].alpha;
-          if (alpha == 0.0f) continue;
-          if (anyHitRnd(seed, uint32_t(curInst), uint32_t(prim)) > alpha) continue;
-        }
-        hit.t = t;
-        hit.u = u;
-        hit.v = v;
-        hit.inst = curInst;
-        hit.prim = prim;
-        hit.front = det > 0.0f ? 1u : 0u;
-        if (ANY) return true;
-      }
-    } else {
-      while (tg.y) {
-        const int b = __ffs(tg.y) - 1;
-        tg.y &= tg.y - 1;
-        const uint32_t ii = __ldg(sc.tlasInstIdx + tg.x + b);
-        const float4* ip = reinterpret_cast<const float4*>(sc.inst + ii);
-        const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-        const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
-        if (ptrs.x == 0ull) continue;
-        if (DETAIL) tc.insts++;
-        // save what is left of this TLAS node, then the marker that brings us back
-        if (tg.y && sp < KF_STACK) stack[sp++] = tg;
-        if ((ng.y & 0xff000000u) && sp < KF_STACK) stack[sp++] = ng;
-        if (sp < KF_STACK) stack[sp++] = make_uint2(0xffffffffu, 0u);
-        // world -> object (contract arithmetic, oracle traceInstance())
-        V3 oo, od;
-        oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
-        oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
-        oo.z = cadd(cdot3(r2.x, r2.y, r2.z, o.x, o.y, o.z), r2.w);
-        od.x = cdot3(r0.x, r0.y, r0.z, d.x, d.y, d.z);
-        od.y = cdot3(r1.x, r1.y, r1.z, d.x, d.y, d.z);
-        od.z = cdot3(r2.x, r2.y, r2.z, d.x, d.y, d.z);
-        r = setupRay(oo, od);
-        nodes = reinterpret_cast<const Node8*>(ptrs.x);
-        nonOpaque = (ptrs.y & 1ull) != 0;
-        tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
-        curInst = int32_t(ii);
-        inBlas = true;
-        ng = make_uint2(0u, 0x80000000u);
-        tg = make_uint2(0u, 0u);
-        break;
-      }
-      if (inBlas) continue;
-    }
-
-    if (!(ng.y & 0xff000000u)) {
-      bool done = false;
-      for (;;) {
-        if (sp == 0) { done = true; break; }
-        const uint2 e = stack[--sp];
-        if (e.y == 0u) {  // sentinel: back to the top level
-          r = setupRay(o, d);
-          nodes = sc.tlasNodes;
-          inBlas = false;
-          continue;
-        }
-        ng = e;
-        break;
-      }
-      if (done) break;
-    }
-  }
-  return hit.inst >= 0;
 }
 
 }  // namespace kf
