@@ -29,6 +29,7 @@
 namespace kf {
 
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
+#define KF_GROUP_RETURN 0x00010000u  // stack entry: a top-level group pushed on entering an instance
 
 struct TraceArgs {
   SceneDev sc;
@@ -80,27 +81,34 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
   uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
 
   bool finished = false;
-  // Next group from the lane's stack: a node group goes to ng, a triangle group to tg; a sentinel
-  // (x, 0) returns to the top level; an empty stack ends the ray.
+  // The stack lives in local memory with its top entry mirrored in registers: a pop hands out the
+  // register copy at once and issues the load of the entry below it, whose latency is then hidden
+  // behind the node step that follows.
+  uint2 top = make_uint2(0u, 0u);
+  auto push = [&](uint2 e) {
+    if (sp < KF_STACK) {
+      stack[sp++] = e;
+      top = e;
+    }
+  };
+  // Next node group from the lane's stack.  A top-level group saved at instance entry carries
+  // KF_GROUP_RETURN: popping it brings the ray back to world space.  An empty stack ends the ray.
   auto popGroup = [&]() {
     for (;;) {
       if (sp == 0) {
         finished = true;
         return;
       }
-      const uint2 e = stack[--sp];
-      if (e.y == 0u) {
+      const uint2 e = top;
+      --sp;
+      if (sp > 0) top = stack[sp - 1];
+      if (e.y & KF_GROUP_RETURN) {
         r = setupRay(o, d);
         nodes = sc.tlasNodes;
         inBlas = false;
-        continue;
+        if (!(e.y & 0xff000000u)) continue;  // that node had no other child left
       }
-      if (e.y & 0xff000000u) {
-        ng = e;
-      } else {
-        tg = e;
-        ng = make_uint2(0u, 0u);
-      }
+      ng = make_uint2(e.x, e.y & ~KF_GROUP_RETURN);
       return;
     }
   };
@@ -169,9 +177,8 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(ip) + 0);
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
           const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);
-          // what is left of this top-level node, then the marker that brings us back
-          if ((ng.y & 0xff000000u) && sp < KF_STACK) stack[sp++] = ng;
-          if (sp < KF_STACK) stack[sp++] = make_uint2(0xffffffffu, 0u);
+          // what is left of this top-level node, marked as the way back to world space
+          push(make_uint2(ng.x, ng.y | KF_GROUP_RETURN));
           // world -> object (contract arithmetic, oracle traceInstance())
           V3 oo, od;
           oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
@@ -198,9 +205,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
       const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;
       if (inBlas || ((hits >> (8 + cslot)) & 1u)) {
         ng.y &= ~(1u << p);
-        if (ng.y & 0xff000000u) {
-          if (sp < KF_STACK) stack[sp++] = ng;
-        }
+        if (ng.y & 0xff000000u) push(ng);
         const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
         uint32_t childBase, primBase, imask;
         const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);

@@ -76,15 +76,22 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
   const uint32_t lox[2] = {n2.x, n2.y}, loy[2] = {n2.z, n2.w}, loz[2] = {n3.x, n3.y};
   const uint32_t hix[2] = {n3.z, n3.w}, hiy[2] = {n4.x, n4.y}, hiz[2] = {n4.z, n4.w};
   const uint32_t meta[2] = {n1.z, n1.w};
+  const uint32_t octinv4 = r.octinv * 0x01010101u;
   uint32_t hitmask = 0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const uint32_t nearx = nx ? hix[h] : lox[h], farx = nx ? lox[h] : hix[h];
     const uint32_t neary = ny ? hiy[h] : loy[h], fary = ny ? loy[h] : hiy[h];
     const uint32_t nearz = nz ? hiz[h] : loz[h], farz = nz ? loz[h] : hiz[h];
+    // four children at a time: where does a hit go in the mask, and which bits does it set?
+    // internal children (meta = 0x20 | 24 + slot) land on bit 24 + (slot ^ octinv), i.e. in traversal
+    // priority order; leaves set `unary count` bits from their offset; empty slots (meta 0) set none.
+    const uint32_t meta4 = meta[h];
+    const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4;  // 1 per internal child
+    const uint32_t index4 = (meta4 ^ (octinv4 & (inner4 * 0xffu))) & 0x1f1f1f1fu;
+    const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const uint32_t m = (meta[h] >> (8 * j)) & 0xffu;
       const float t0x = fmaf(planeFloat(nearx, j), ax, bx);
       const float t0y = fmaf(planeFloat(neary, j), ay, by);
       const float t0z = fmaf(planeFloat(nearz, j), az, bz);
@@ -93,13 +100,8 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
       const float t1z = fmaf(planeFloat(farz, j), az, bz);
       const float t0 = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       const float t1 = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      if (m != 0 && t0 <= t1) {
-        const int slot = h * 4 + j;
-        if ((imask >> slot) & 1u)
-          hitmask |= 1u << (24 + (slot ^ r.octinv));
-        else
-          hitmask |= (m >> 5) << (m & 31u);
-      }
+      const uint32_t bits = (bits4 >> (8 * j)) & 0xffu, index = (index4 >> (8 * j)) & 0xffu;
+      hitmask |= (t0 <= t1) ? (bits << index) : 0u;
     }
   }
   return hitmask;
