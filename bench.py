@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--scene", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-spp", type=int, default=1)
+    ap.add_argument("--cpu-sample-spp", type=int, default=8)
     return ap.parse_args()
 
 
@@ -135,9 +135,21 @@ class DevArray:
                                          "version": 3, "strides": None}
 
 
+def trace_closest_bytes(cnt, stats):
+    """Algorithmic bytes of the closest-hit traversal stage (the dominant kernel, k_wf_trace<closest>):
+    its share of SURVEY.md §8.5 -- nodes, triangles and instance records it fetched, plus 32 B ray read
+    and 16 B hit record write per extension ray."""
+    ext = int(cnt["extensionRays"])
+    n = int(cnt["nodeVisits"]) - int(cnt["shadowNodeVisits"])
+    t = int(cnt["triangleTests"]) - int(cnt["shadowTriangleTests"])
+    i = int(cnt["instanceVisits"]) - int(cnt["shadowInstanceVisits"])
+    b = int(stats["nodeBytes"]) * n + int(stats["triangleBytes"]) * t + int(stats["instanceBytes"]) * i
+    return b + ext * (32 + 16), {"nodes": n / max(ext, 1), "triangles": t / max(ext, 1), "instances": i / max(ext, 1)}
+
+
 def algorithmic_bytes(cnt, stats, n_pixels):
     """SURVEY.md §8.5 accounting: bytes a frame must move given what it visited (layout constants from
-    kfrtGetBvhStats: 80 B wide node, 48 B triangle, 64 B instance record)."""
+    kfrtGetBvhStats: 80 B wide node, 48 B triangle, 80 B instance record)."""
     ext, sh, hits = int(cnt["extensionRays"]), int(cnt["shadowRays"]), int(cnt["extensionHits"])
     rays = ext + sh
     b = (int(stats["nodeBytes"]) * int(cnt["nodeVisits"]) + int(stats["triangleBytes"]) * int(cnt["triangleTests"]) +
@@ -273,13 +285,19 @@ def main():
     events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     rays_total, launches = 0, 0
     counters = []
+    stage_ms, stage_launches = {}, {}
+    ctx.set_stage_timers(True)  # one event record per stage launch, on the same stream
     for k in range(args.steps):
         frame(args.warmup + k, events[k])
         c = ctx.counters()  # synchronises; outside the event brackets
         counters.append(c)
+        for name, (ms, n) in ctx.stage_times().items():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+            stage_launches[name] = stage_launches.get(name, 0) + n
         launches += int(c["kernelLaunches"]) if rank == 0 else 1
         flush.zero_()  # L2 flush between timed steps
     barrier()
+    ctx.set_stage_timers(False)
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [events[k][0].elapsed_time(events[k][2]) for k in range(args.steps)]
     render_ms = [events[k][0].elapsed_time(events[k][1]) for k in range(args.steps)]
@@ -305,21 +323,35 @@ def main():
         ctx.set_detail_counters(False)
         abytes, rays = algorithmic_bytes(detail, stats, n_pixels)
         peak, peak_src = measured_peaks()
-        dur = statistics.mean(render_ms) * 1e-3
-        achieved = abytes / dur / 1e9
+        # dominant kernel: the closest-hit traversal stage.  Bytes from the detail pass (same seeds as
+        # the last timed step), launch count and duration from the stage events of the timed steps.
+        kname = "trace_closest"
+        k_launches = max(stage_launches.get(kname, 0) // args.steps, 1)
+        k_ms = stage_ms.get(kname, 0.0) / max(stage_launches.get(kname, 0), 1)
+        kbytes, kper = trace_closest_bytes(detail, stats)
+        kbytes_per_launch = kbytes / k_launches
+        achieved = kbytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
+        dur = statistics.mean(render_ms) * 1e-3
+        frame_achieved = abytes / dur / 1e9
+        total_stage = sum(stage_ms.values()) or 1.0
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "trace (ray generation + traversal + shading)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
-                "bytes_per_ray": abytes / max(rays, 1),
-                "per_ray": {"nodes": int(detail["nodeVisits"]) / max(rays, 1),
-                            "triangles": int(detail["triangleTests"]) / max(rays, 1),
-                            "instances": int(detail["instanceVisits"]) / max(rays, 1)},
-                "kernel_ms": statistics.mean(render_ms)}
+                "traffic": traffic, "kernel": "k_wf_trace<closest hit> (extension-ray traversal stage)",
+                "peak_source": peak_src + ", burst copy figure",
+                "algorithmic_bytes_per_launch": kbytes_per_launch, "launches_per_step": k_launches,
+                "launch_ms": k_ms, "per_ray": kper,
+                "share_of_step": stage_ms.get(kname, 0.0) / total_stage,
+                "stages_ms_per_step": {n: v / args.steps for n, v in stage_ms.items() if v > 0},
+                "frame": {"achieved": frame_achieved, "frac": frame_achieved / peak,
+                          "algorithmic_bytes_per_step": abytes, "bytes_per_ray": abytes / max(rays, 1),
+                          "per_ray": {"nodes": int(detail["nodeVisits"]) / max(rays, 1),
+                                      "triangles": int(detail["triangleTests"]) / max(rays, 1),
+                                      "instances": int(detail["instanceVisits"]) / max(rays, 1)},
+                          "render_ms": statistics.mean(render_ms)}}
 
     # ---- e2e: the user-facing call (Kuafu::run + downloadLatestFrame) with host buffers
     e2e_t, e2e_rays = 0.0, 0

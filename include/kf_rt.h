@@ -267,6 +267,26 @@ KFRT_API int kfrtDownloadAux(KfrtContext* ctx, uint32_t camera, int kind, void* 
  * wants to run a collective or a copy on it without a host round trip. */
 KFRT_API int kfrtGetDeviceBuffer(KfrtContext* ctx, int kind, void** devicePtr, size_t* nbytes);
 
+/* Per-stage device time of the last kfrtRender, for the roofline accounting of single kernels.
+ * With timers on, kfrtRender records a CUDA event on the context's stream before every stage launch;
+ * kfrtGetStageTimes waits for the last one and sums the event-to-event durations per stage. */
+enum {
+  KFRT_STAGE_RAYGEN = 0,          /* k_wf_raygen */
+  KFRT_STAGE_TRACE_CLOSEST = 1,   /* k_wf_trace<closest hit>: extension rays */
+  KFRT_STAGE_SHADE = 2,           /* k_wf_shade */
+  KFRT_STAGE_TRACE_OCCLUSION = 3, /* k_wf_trace<first hit>: shadow rays */
+  KFRT_STAGE_SHADOW_RESOLVE = 4,  /* k_wf_shadow_resolve */
+  KFRT_STAGE_FINISH = 5,          /* k_wf_finish */
+  KFRT_STAGE_OTHER = 6,
+  KFRT_STAGE_END = 7
+};
+typedef struct KfrtStageTimes {
+  double ms[8];          /* total device milliseconds per stage */
+  uint64_t launches[8];  /* kernel launches per stage */
+} KfrtStageTimes;
+KFRT_API int kfrtSetStageTimers(KfrtContext* ctx, int on);
+KFRT_API int kfrtGetStageTimes(KfrtContext* ctx, KfrtStageTimes* out);
+
 /* detail != 0 additionally counts node/triangle/instance/texture fetches (slower kernels). */
 KFRT_API int kfrtSetDetailCounters(KfrtContext* ctx, int detail);
 KFRT_API int kfrtGetCounters(KfrtContext* ctx, KfrtCounters* out);

@@ -154,7 +154,26 @@ struct KfrtContext {
   DevBuf<uint32_t> wfQueue0, wfQueue1, wfShadowQ0, wfShadowQ1, wfCounts;
   int gridTrace[4] = {0, 0, 0, 0}, gridShade[4] = {0, 0, 0, 0}, gridShadow[4] = {0, 0, 0, 0}, gridRaygen = 0;
   KfrtCounters lastCounters{};
+  // per-stage device timers (kfrtSetStageTimers): one event before every launch + one at the end
+  bool stageTimers = false;
+  std::vector<cudaEvent_t> stageEvents;
+  std::vector<int> stageOf;  // stage launched after event i
+  size_t stageUsed = 0;
 };
+
+// Marks the start of a launch of `stage` on the context's stream (no-op unless timers are on).
+static void stageMark(KfrtContext* ctx, int stage) {
+  if (!ctx->stageTimers) return;
+  if (ctx->stageUsed == ctx->stageEvents.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->stageEvents.push_back(e);
+    ctx->stageOf.push_back(0);
+  }
+  ctx->stageOf[ctx->stageUsed] = stage;
+  cudaEventRecord(ctx->stageEvents[ctx->stageUsed], ctx->stream);
+  ctx->stageUsed++;
+}
 
 #define KF_FAIL(ctx, code, msg)  \
   do {                           \
@@ -505,6 +524,7 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->wfStateC.release(); ctx->wfShadowL.release(); ctx->wfShadowC.release(); ctx->wfCtx.release();
   ctx->wfHitB.release(); ctx->wfQueue0.release(); ctx->wfQueue1.release(); ctx->wfShadowQ0.release();
   ctx->wfShadowQ1.release(); ctx->wfCounts.release();
+  for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
   delete ctx;
   return KFRT_OK;
@@ -891,6 +911,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     a.batchBegin = b0;
     a.batchCount = std::min(batch, ra.s1 - b0);
     KF_CUDA(ctx, cudaMemsetAsync(a.b.counts, 0, 8 * sizeof(uint32_t), st));
+    stageMark(ctx, KFRT_STAGE_RAYGEN);
     k_wf_raygen<<<ctx->gridRaygen, 256, 0, st>>>(a);
     ctx->launches++;
     for (uint32_t depth = 0; depth <= ra.pc.maxPathDepth; depth++) {
@@ -912,8 +933,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.counters = a.counters;
       te.rayCounter = 1;
       te.detailBase = 4;
+      stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
       else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
+      stageMark(ctx, KFRT_STAGE_SHADE);
       switch (variant) {
         case 0: k_wf_shade<false, false><<<ctx->gridShade[0], 128, 0, st>>>(a, q, depth); break;
         case 1: k_wf_shade<false, true><<<ctx->gridShade[1], 128, 0, st>>>(a, q, depth); break;
@@ -932,8 +955,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
         ts.clear0 = ts.clear1 = ts.clear2 = nullptr;
         ts.rayCounter = 2;
         ts.detailBase = 8;
+        stageMark(ctx, KFRT_STAGE_TRACE_OCCLUSION);
         if (d) k_wf_trace<true, true><<<ctx->gridTrace[3], 128, 0, st>>>(ts);
         else k_wf_trace<true, false><<<ctx->gridTrace[2], 128, 0, st>>>(ts);
+        stageMark(ctx, KFRT_STAGE_SHADOW_RESOLVE);
         switch (variant) {
           case 0: k_wf_shadow_resolve<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
           case 1: k_wf_shadow_resolve<false, true><<<ctx->gridShadow[1], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
@@ -942,14 +967,17 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
         }
         ctx->launches += 2;
         if (multi && l + 1 < rounds) {
+          stageMark(ctx, KFRT_STAGE_OTHER);
           k_wf_clear_count<<<1, 1, 0, st>>>(a.b.counts + 2 + sq);
           ctx->launches++;
         }
       }
     }
+    stageMark(ctx, KFRT_STAGE_FINISH);
     k_wf_finish<<<gridFor(slotsPerSample, 256), 256, 0, st>>>(a);
     ctx->launches++;
   }
+  stageMark(ctx, KFRT_STAGE_END);
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -1032,6 +1060,7 @@ int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, u
   a.hitT = ctx->hitT.p;
   a.depth = ctx->depth.p;
   a.counters = ctx->counters.p;
+  ctx->stageUsed = 0;
   rc = renderWavefront(ctx, a);
   if (rc) return rc;
   ctx->lastPc = *pc;
@@ -1133,6 +1162,30 @@ int kfrtGetDeviceBuffer(KfrtContext* ctx, int kind, void** devicePtr, size_t* nb
 int kfrtSetDetailCounters(KfrtContext* ctx, int detail) {
   KF_CHECK_CTX(ctx);
   ctx->detail = detail ? 1 : 0;
+  return KFRT_OK;
+}
+
+int kfrtSetStageTimers(KfrtContext* ctx, int on) {
+  KF_CHECK_CTX(ctx);
+  ctx->stageTimers = on != 0;
+  ctx->stageUsed = 0;
+  return KFRT_OK;
+}
+
+int kfrtGetStageTimes(KfrtContext* ctx, KfrtStageTimes* out) {
+  KF_CHECK_CTX(ctx);
+  if (!out) KF_FAIL(ctx, KFRT_ERR_INVALID, "null stage times");
+  std::memset(out, 0, sizeof(*out));
+  if (ctx->stageUsed < 2) return KFRT_OK;
+  KF_CUDA(ctx, cudaEventSynchronize(ctx->stageEvents[ctx->stageUsed - 1]));
+  for (size_t i = 0; i + 1 < ctx->stageUsed; i++) {
+    const int stage = ctx->stageOf[i];
+    if (stage < 0 || stage >= KFRT_STAGE_END) continue;
+    float ms = 0.0f;
+    KF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->stageEvents[i], ctx->stageEvents[i + 1]));
+    out->ms[stage] += ms;
+    out->launches[stage]++;
+  }
   return KFRT_OK;
 }
 

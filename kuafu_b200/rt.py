@@ -44,6 +44,7 @@ def load():
         "kfrtDownloadAux": [vp, u32, i32, vp, sz],
         "kfrtGetDeviceBuffer": [vp, i32, C.POINTER(vp), C.POINTER(sz)],
         "kfrtSetDetailCounters": [vp, i32], "kfrtGetCounters": [vp, vp],
+        "kfrtSetStageTimers": [vp, i32], "kfrtGetStageTimes": [vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -210,6 +211,15 @@ class Context:
 
     def set_detail_counters(self, on):
         self._ck(self.lib.kfrtSetDetailCounters(self.h, int(on)))
+
+    def set_stage_timers(self, on):
+        self._ck(self.lib.kfrtSetStageTimers(self.h, int(on)))
+
+    def stage_times(self):
+        """{stage name: (total device ms, launches)} of the last render (needs set_stage_timers(True))."""
+        t = np.zeros((), wire.STAGE_TIMES)
+        self._ck(self.lib.kfrtGetStageTimes(self.h, _ptr(t)))
+        return {n: (float(t["ms"][i]), int(t["launches"][i])) for i, n in enumerate(wire.STAGE_NAMES)}
 
     def counters(self):
         c = np.zeros((), wire.COUNTERS)

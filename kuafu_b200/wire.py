@@ -54,3 +54,6 @@ def push_constants(clear_color=(0, 0, 0, 1), frame_count=0, spp=1, max_depth=8, 
     pc["russianRouletteMinBounces"] = rr_min
     pc["nextEventEstimation"] = 1
     return pc
+
+STAGE_TIMES = np.dtype([("ms", "<f8", 8), ("launches", "<u8", 8)])
+STAGE_NAMES = ("raygen", "trace_closest", "shade", "trace_occlusion", "shadow_resolve", "finish", "other")
