@@ -147,6 +147,7 @@ struct KfrtContext {
   // wavefront scheduler state
   int numSMs = 148;
   size_t batchSlotTarget = size_t(16) << 20;
+  int refillIdle = KF_REFILL_IDLE;
   size_t wfSlots = 0;
   bool wfMulti = false;
   DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
@@ -474,6 +475,7 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
   }
   ctx->stream = ctx->ownStream;
   ctx->numSMs = prop.multiProcessorCount;
+  if (const char* e = std::getenv("KFRT_REFILL_IDLE")) ctx->refillIdle = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
     if (v > 0) ctx->batchSlotTarget = size_t(v);
@@ -933,6 +935,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.counters = a.counters;
       te.rayCounter = 1;
       te.detailBase = 4;
+      te.refillIdle = ctx->refillIdle;
       stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
       else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);

@@ -47,6 +47,7 @@ struct TraceArgs {
   unsigned long long* counters;
   int rayCounter;            // counters[] index that receives the number of rays of this stage
   int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
+  int refillIdle;            // refill a warp once this many of its lanes are without a ray
 };
 
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
@@ -85,6 +86,8 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
   // register copy at once and issues the load of the entry below it, whose latency is then hidden
   // behind the node step that follows.
   uint2 top = make_uint2(0u, 0u);
+  float wix = 0.0f, wiy = 0.0f, wiz = 0.0f;  // world-space reciprocal direction (r is per-space)
+  uint32_t woct = 0;
   auto push = [&](uint2 e) {
     if (sp < KF_STACK) {
       stack[sp++] = e;
@@ -103,7 +106,11 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
       --sp;
       if (sp > 0) top = stack[sp - 1];
       if (e.y & KF_GROUP_RETURN) {
-        r = setupRay(o, d);
+        // back to world space: origin/direction from registers, the reciprocals saved at entry
+        r.ox = o.x; r.oy = o.y; r.oz = o.z;
+        r.dx = d.x; r.dy = d.y; r.dz = d.z;
+        r.ix = wix; r.iy = wiy; r.iz = wiz;
+        r.octinv = woct;
         nodes = sc.tlasNodes;
         inBlas = false;
         if (!(e.y & 0xff000000u)) continue;  // that node had no other child left
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
     // ---- refill: lanes without a ray take consecutive queue positions -------------------------
     const uint32_t idle = __ballot_sync(0xffffffffu, !active);
     if (idle) {
-      if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= KF_REFILL_IDLE)) {
+      if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= a.refillIdle)) {
         const uint32_t want = uint32_t(__popc(idle));
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(a.fetch, want);
@@ -135,6 +142,8 @@ __global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
             hit.prim = -1;
             hit.front = 0;
             r = setupRay(o, d);
+            wix = r.ix; wiy = r.iy; wiz = r.iz;
+            woct = r.octinv;
             nodes = sc.tlasNodes;
             inBlas = false;
             nonOpaque = false;

@@ -27,11 +27,14 @@ struct RaySetup {
   uint32_t octinv;   // bit k set when direction k is >= 0
 };
 
-// Reciprocals feed the (conservative) box tests only, so the approximate MUFU.RCP is enough.
-KF_D float boxRcp(float x) {
-  const float eps = 1e-20f;
-  return __fdividef(1.0f, fabsf(x) > eps ? x : copysignf(eps, x));
+// Reciprocals feed the (conservative) box tests only, so the approximate MUFU.RCP is enough; the
+// clamp keeps a zero direction component finite (+-1e20) so that no slab product becomes NaN.
+KF_D float __frcp_rn_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+KF_D float boxRcp(float x) { return fminf(fmaxf(__frcp_rn_approx(x), -1e20f), 1e20f); }
 KF_D RaySetup setupRay(V3 o, V3 d) {
   RaySetup r;
   r.ox = o.x; r.oy = o.y; r.oz = o.z;
