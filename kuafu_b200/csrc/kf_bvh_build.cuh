@@ -124,6 +124,8 @@ struct BlasInfo {
   const Node8* nodes;
   const Tri48* tris;
   const KfrtVertex* verts;
+  const uint32_t* idx;
+  const uint32_t* matIndex;
   float box[6];
   uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque
   uint32_t nVerts;
@@ -164,21 +166,19 @@ __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_
     for (int c = 0; c < 4; c++) rec.inv[4 * r + c] = inv[r][c];
   const uint32_t g = insts[i].geometryIndex;
   const bool usable = g < nBlas && (blas[g].flags & 1u);
-  if (usable) {
-    rec.nodes = blas[g].nodes;
-    rec.tris = reinterpret_cast<const Tri48*>(reinterpret_cast<uintptr_t>(blas[g].tris) |
-                                              ((blas[g].flags & 2u) ? 1ull : 0ull));
-  } else {
-    rec.nodes = nullptr;
-    rec.tris = nullptr;
-  }
+  rec.verts = g < nBlas ? blas[g].verts : nullptr;
+  rec.idx = g < nBlas ? blas[g].idx : nullptr;
+  rec.matIndex = g < nBlas ? blas[g].matIndex : nullptr;
+  rec.pad = 0;
   recs[i] = rec;
   // the record the traversal reads, in the top-level node array
   InstNode in;
 #pragma unroll
   for (int k = 0; k < 12; k++) in.inv[k] = rec.inv[k];
-  in.nodes = rec.nodes;
-  in.tris = rec.tris;
+  in.nodes = usable ? blas[g].nodes : nullptr;
+  in.tris = usable ? reinterpret_cast<const Tri48*>(reinterpret_cast<uintptr_t>(blas[g].tris) |
+                                                    ((blas[g].flags & 2u) ? 1ull : 0ull))
+                   : nullptr;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     in.box[k] = __half_as_ushort(__float2half_rd(primBox[6 * i + k]));

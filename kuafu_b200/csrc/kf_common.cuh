@@ -125,13 +125,17 @@ struct __align__(16) Tri48 {
 };
 static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 
-// Per-instance shading record (world->object for the normal transform), indexed by instance.
+// Per-instance shading record, indexed by instance: world->object (for the normal transform) and the
+// geometry's attribute tables, so that the attribute gather of a hit is instance -> indices ->
+// vertices with no detour over the instance SSBO and the geometry table.  80 bytes = 5 x 16 B loads.
 struct __align__(16) InstRec {
-  float inv[12];          // world->object, 3 rows x 4 columns
-  const Node8* nodes;     // BLAS nodes (root = nodes[0]); NULL when the geometry is hidden/empty
-  const Tri48* tris;      // BLAS triangles in leaf order; bit 0 set == non-opaque geometry
+  float inv[12];            // world->object, 3 rows x 4 columns
+  const KfrtVertex* verts;  // geometry tables (reference PathTrace.rchit:66-98)
+  const uint32_t* idx;
+  const uint32_t* matIndex;
+  uint64_t pad;
 };
-static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
+static_assert(sizeof(InstRec) == 80, "InstRec must be 80 bytes");
 
 // Instance record as it sits in the top-level node array (same 80-byte stride as a Node8, addressed
 // like an internal child): what a ray needs to enter a bottom-level structure, 5 x 16 B loads.
@@ -174,6 +178,7 @@ struct SceneDev {
   const KfrtDirectionalLight* dl;
   const KfrtPointLights* pl;
   const KfrtActiveLights* al;
+  unsigned long long lightMask;  // bit k: light slot k (0 directional, 1..32 point, 33..40 active) is on
 };
 
 struct Hit {

@@ -122,6 +122,7 @@ struct KfrtContext {
   DevBuf<KfrtPointLights> pl;
   DevBuf<KfrtActiveLights> al;
   uint32_t nLightSlots = 0;
+  unsigned long long lightMask = 0;
   DevBuf<float> srgbToLinear, srgbThreshold;
 
   std::vector<KfrtInstance> instHost;
@@ -347,6 +348,8 @@ static int uploadTables(KfrtContext* ctx) {
     infos[i].nodes = g.nodes;
     infos[i].tris = g.tris;
     infos[i].verts = g.verts;
+    infos[i].idx = g.idx;
+    infos[i].matIndex = g.matIndex;
     infos[i].nVerts = g.nVerts;
     std::memcpy(infos[i].box, g.box, sizeof(g.box));
     infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u);
@@ -665,11 +668,14 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
   if (points) p = *points;
   if (actives) a = *actives;
   uint32_t slots = 0;
-  if (d.rgbs[0] * d.rgbs[3] != 0 || d.rgbs[1] * d.rgbs[3] != 0 || d.rgbs[2] * d.rgbs[3] != 0) slots++;
+  unsigned long long mask = 0;
+  if (d.rgbs[0] * d.rgbs[3] != 0 || d.rgbs[1] * d.rgbs[3] != 0 || d.rgbs[2] * d.rgbs[3] != 0) mask |= 1ull;
   for (int i = 0; i < KFRT_MAX_POINT_LIGHTS; i++)
-    if (p.rgbs[i][3] > 0) slots++;
+    if (p.rgbs[i][3] > 0) mask |= 1ull << (1 + i);
   for (int i = 0; i < KFRT_MAX_ACTIVE_LIGHTS; i++)
-    if (a.front[i][3] > 0) slots++;
+    if (a.front[i][3] > 0) mask |= 1ull << (33 + i);
+  for (unsigned long long m = mask; m; m &= m - 1) slots++;
+  ctx->lightMask = mask;
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->dl.p, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->pl.p, &p, sizeof(p), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->al.p, &a, sizeof(a), cudaMemcpyHostToDevice, ctx->stream));
@@ -1025,6 +1031,7 @@ static SceneDev sceneDev(KfrtContext* ctx) {
   sc.dl = ctx->dl.p;
   sc.pl = ctx->pl.p;
   sc.al = ctx->al.p;
+  sc.lightMask = ctx->lightMask;
   return sc;
 }
 

@@ -188,8 +188,12 @@ KF_D bool shadeSurface(const SceneDev& sc, const Hit& h, V3 rayO, V3 rayD, uint3
                        V3& L, V3& weight, V3& albedo, V3& emission, uint32_t& texFetches) {
   const float4* ip = reinterpret_cast<const float4*>(sc.inst + h.inst);
   const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-  const uint32_t geometryIndex = sc.instSsbo[h.inst].geometryIndex;
-  const GeomRec g = sc.geoms[geometryIndex];
+  const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
+  const ulonglong2 p23 = __ldg(reinterpret_cast<const ulonglong2*>(ip + 4));
+  struct { const KfrtVertex* verts; const uint32_t* idx; const uint32_t* matIndex; } g;
+  g.verts = reinterpret_cast<const KfrtVertex*>(p01.x);
+  g.idx = reinterpret_cast<const uint32_t*>(p01.y);
+  g.matIndex = reinterpret_cast<const uint32_t*>(p23.x);
   const uint32_t i0 = __ldg(g.idx + 3 * h.prim + 0), i1 = __ldg(g.idx + 3 * h.prim + 1),
                  i2 = __ldg(g.idx + 3 * h.prim + 2);
   // vertex = 3 x float4: (pos.xyz, n.x) (n.y, n.z, c.r, c.g) (c.b, u, v, pad)   [rchit:52-64]
@@ -359,7 +363,15 @@ KF_D V3 calcDirect(const Surface& sf, V3 L, V3 lightEmission, uint32_t& seed) {
 // consuming exactly the random numbers the reference consumes for them.
 KF_D bool nextLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& k, V3& L, float& maxDist,
                     V3& lightEmission, uint32_t& texFetches) {
-  for (; k < KF_NUM_LIGHT_SLOTS; k++) {
+  for (;; k++) {
+    // jump to the next slot that is switched on at all (sc.lightMask, computed by kfrtSetLights from
+    // the same conditions the reference tests before it draws any random number for a light)
+    const unsigned long long pending = k < KF_NUM_LIGHT_SLOTS ? (sc.lightMask >> k) : 0ull;
+    if (pending == 0ull) {
+      k = KF_NUM_LIGHT_SLOTS;
+      return false;
+    }
+    k += __ffsll((long long)pending) - 1;
     if (k == 0) {  // rchit:204-223
       const float4 dir = __ldg(reinterpret_cast<const float4*>(sc.dl->direction));
       const float4 rgbs = __ldg(reinterpret_cast<const float4*>(sc.dl->rgbs));
@@ -431,7 +443,6 @@ KF_D bool nextLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& 
     // traceShadowRay (rchit:175-200): below the horizon counts as shadowed, no ray, no random draw
     if (dot(sf.N, L) > 0.0f) return true;
   }
-  return false;
 }
 
 // Camera ray of one sample (reference PathTrace.rgen:35-56), contract arithmetic: the primary-ray

@@ -29,6 +29,9 @@
 namespace kf {
 
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
+#ifndef KF_TRACE_MIN_BLOCKS
+#define KF_TRACE_MIN_BLOCKS 7
+#endif
 #define KF_GROUP_RETURN 0x00010000u  // stack entry: a top-level group pushed on entering an instance
 
 struct TraceArgs {
@@ -53,7 +56,7 @@ struct TraceArgs {
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
 // SkipClosestHitShader) for every ray of the queue.
 template <bool ANY, bool DETAIL>
-__global__ void __launch_bounds__(128) k_wf_trace(TraceArgs a) {
+__global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs a) {
   const uint32_t count = *a.count;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.clear0) *a.clear0 = 0;
