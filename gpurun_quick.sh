@@ -1,4 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/counters.py million 0 0 8 2>&1 | tail -4
-python tools/counters.py articulated 0 0 2 2>&1 | tail -4
-python tools/counters.py spheres 0 0 8 2>&1 | tail -4
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25
