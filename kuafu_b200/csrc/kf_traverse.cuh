@@ -49,8 +49,11 @@ KF_D RaySetup setupRay(V3 o, V3 d) {
 // Quantised plane byte j of word w as the float 1 + q * 2^-15: one PRMT drops the byte into the
 // second mantissa byte of 1.0f, so the dequantisation never touches the (quarter-rate) int->float
 // conversion pipe.  t = f * A + B with A = 2^15 * scale * idir, B = (origin term) - A.
+// The constant goes in PRMT's first operand (always a register, loaded once) and the data word in
+// the third, so that the selector can be an immediate; the other way round ptxas makes the constant
+// the immediate and re-materialises the selector into a register before each of the 48 PRMTs of a node.
 KF_D float planeFloat(uint32_t w, int j) {
-  return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
+  return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3200u | (uint32_t(4 + j) << 4)));
 }
 
 // Intersects the 8 quantised child boxes of `node`; returns the CWBVH hit mask:

@@ -25,6 +25,11 @@ print(f"{scene}: paths {int(c['paths'])}, extension rays {ext} ({int(c['extensio
 print(f"  closest-hit per ray: nodes {n/max(ext,1):.2f} tris {t/max(ext,1):.2f} instances {i/max(ext,1):.2f}")
 print(f"  occlusion   per ray: nodes {sn/max(sh,1):.2f} tris {st/max(sh,1):.2f} instances {si/max(sh,1):.2f}")
 ts = []
-for k in range(3):
+ctx.set_stage_timers(True)
+acc = {}
+for k in range(5):
     t0 = time.perf_counter(); r.run(); ctx.synchronize(); ts.append(time.perf_counter() - t0)
+    for n, (ms, _) in ctx.stage_times().items():
+        acc.setdefault(n, []).append(ms)
 print(f"  frame {min(ts)*1e3:.2f} ms -> {(ext+sh)/min(ts)/1e6:.1f} Mrays/s (wall, incl. resolve)")
+print("  stages (min of 5, ms): " + ", ".join(f"{n} {min(v):.2f}" for n, v in acc.items() if min(v) > 0))
