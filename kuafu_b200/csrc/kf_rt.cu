@@ -147,7 +147,7 @@ struct KfrtContext {
   uint64_t launches = 0;
   // wavefront scheduler state
   int numSMs = 148;
-  size_t batchSlotTarget = size_t(16) << 20;
+  size_t batchSlotTarget = size_t(32) << 20;
   int refillIdle = KF_REFILL_IDLE;
   size_t wfSlots = 0;
   bool wfMulti = false;

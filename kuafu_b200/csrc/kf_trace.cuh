@@ -32,7 +32,6 @@ namespace kf {
 #ifndef KF_TRACE_MIN_BLOCKS
 #define KF_TRACE_MIN_BLOCKS 7
 #endif
-#define KF_GROUP_RETURN 0x00010000u  // stack entry: a top-level group pushed on entering an instance
 
 struct TraceArgs {
   SceneDev sc;
@@ -97,30 +96,26 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
       top = e;
     }
   };
-  // Next node group from the lane's stack.  A top-level group saved at instance entry carries
-  // KF_GROUP_RETURN: popping it brings the ray back to world space.  An empty stack ends the ray.
+  // Next node group from the lane's stack.  spBlas is the stack height at instance entry: popping
+  // at that height means the bottom level is exhausted and the ray returns to world space.  An empty
+  // stack ends the ray.
+  int spBlas = 0;
   auto popGroup = [&]() {
-    for (;;) {
-      if (sp == 0) {
-        finished = true;
-        return;
-      }
-      const uint2 e = top;
-      --sp;
-      if (sp > 0) top = stack[sp - 1];
-      if (e.y & KF_GROUP_RETURN) {
-        // back to world space: origin/direction from registers, the reciprocals saved at entry
-        r.ox = o.x; r.oy = o.y; r.oz = o.z;
-        r.dx = d.x; r.dy = d.y; r.dz = d.z;
-        r.ix = wix; r.iy = wiy; r.iz = wiz;
-        r.octinv = woct;
-        nodes = sc.tlasNodes;
-        inBlas = false;
-        if (!(e.y & 0xff000000u)) continue;  // that node had no other child left
-      }
-      ng = make_uint2(e.x, e.y & ~KF_GROUP_RETURN);
+    if (inBlas && sp == spBlas) {
+      r.ox = o.x; r.oy = o.y; r.oz = o.z;
+      r.dx = d.x; r.dy = d.y; r.dz = d.z;
+      r.ix = wix; r.iy = wiy; r.iz = wiz;
+      r.octinv = woct;
+      nodes = sc.tlasNodes;
+      inBlas = false;
+    }
+    if (sp == 0) {
+      finished = true;
       return;
     }
+    ng = top;
+    --sp;
+    if (sp > 0) top = stack[sp - 1];
   };
 
   for (;;) {
@@ -189,8 +184,9 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(ip) + 0);
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
           const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);
-          // what is left of this top-level node, marked as the way back to world space
-          push(make_uint2(ng.x, ng.y | KF_GROUP_RETURN));
+          // what is left of this top-level node waits on the stack, below the bottom-level entries
+          if (ng.y & 0xff000000u) push(ng);
+          spBlas = sp;
           // world -> object (contract arithmetic, oracle traceInstance())
           V3 oo, od;
           oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
@@ -227,9 +223,6 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
         tg = make_uint2(primBase, inBlas ? (hm & 0x00ffffffu) : 0u);
       }
     }
-    // ---- pop: lanes with nothing in hand take the next group from their stack ------------------
-    if (active && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
-
     // ---- triangle phase (bottom level): one leaf triangle per lane -------------------------------
     if (active && !finished && tg.y != 0u) {
       const int b = __ffs(tg.y) - 1;
@@ -268,9 +261,9 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
         hit.front = det > 0.0f ? 1u : 0u;
         if (ANY) finished = true;
       }
-      // a lane that has just used up its leaf group pops here, so that it can step next iteration
-      if (!finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
     }
+    // ---- pop: lanes with nothing left in hand take the next group from their stack ----------------
+    if (active && !finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
 
     if (finished) {
       if (ANY) {

@@ -106,7 +106,7 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
       const float t1z = fmaf(planeFloat(farz, j), az, bz);
       const float t0 = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       const float t1 = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      const uint32_t bits = (bits4 >> (8 * j)) & 0xffu, index = (index4 >> (8 * j)) & 0xffu;
+      const uint32_t bits = __byte_perm(bits4, 0u, 0x4440u | uint32_t(j)), index = __byte_perm(index4, 0u, 0x4440u | uint32_t(j));
       hitmask |= (t0 <= t1) ? (bits << index) : 0u;
     }
   }
