@@ -5,7 +5,7 @@
 // Pipeline (all kernels here; the host only sequences launches):
 //   primitive boxes -> scene box (ordered-int atomics) -> 63-bit Morton keys -> LSD radix sort
 //   -> Karras LBVH hierarchy -> bottom-up boxes (atomic arrival counters)
-//   -> level-by-level collapse into 8-wide nodes (largest-area-first expansion, leaves <= 3 prims,
+//   -> level-by-level collapse into 8-wide nodes (largest-area-first expansion, leaves <= 2 prims,
 //      octant slot assignment, 8-bit quantisation) -> triangles re-laid in leaf order.
 // Refit keeps the binary topology and the slot assignment, recomputes boxes bottom-up and
 // re-quantises every wide node.
@@ -499,7 +499,7 @@ KF_D void quantiseNode(Node8& nd, const Box6& nbIn, const Box6* slotBox, uint32_
 }
 
 #define KF_MEMBER_EMPTY 0x7fffffff
-#define KF_LEAF_MAX 3
+#define KF_LEAF_MAX 2
 
 struct CollapseArgs {
   int n;                      // primitives
