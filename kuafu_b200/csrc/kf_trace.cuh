@@ -29,9 +29,6 @@
 namespace kf {
 
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
-#ifndef KF_TRACE_MIN_BLOCKS
-#define KF_TRACE_MIN_BLOCKS 7
-#endif
 
 struct TraceArgs {
   SceneDev sc;
@@ -55,7 +52,9 @@ struct TraceArgs {
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
 // SkipClosestHitShader) for every ray of the queue.
 template <bool ANY, bool DETAIL>
-__global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs a) {
+// Occlusion rays carry no (u, v, prim) and fit 64 registers (8 blocks / SM) without spilling; the
+// closest-hit variant runs best at 72 registers (7 blocks / SM).
+__global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   const uint32_t count = *a.count;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (a.clear0) *a.clear0 = 0;
@@ -73,8 +72,11 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
   int sp = 0;
   bool active = false, exhausted = false;
   uint32_t slot = 0;
-  V3 o = mk3(0.0f), d = mk3(0.0f);
-  RaySetup r = setupRay(o, mk3(1.0f));
+  RaySetup r = setupRay(mk3(0.0f), mk3(1.0f));
+  // The world-space ray setup waits in shared memory while the lane is inside a bottom-level
+  // structure (r then holds the object-space ray): ten registers less per lane.
+  __shared__ float sWorld[10][128];
+  const uint32_t tid = threadIdx.x;
   Hit hit;
   hit.t = 0.0f; hit.u = hit.v = 0.0f; hit.inst = hit.prim = -1; hit.front = 0;
   const Node8* nodes = sc.tlasNodes;
@@ -88,8 +90,6 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
   // register copy at once and issues the load of the entry below it, whose latency is then hidden
   // behind the node step that follows.
   uint2 top = make_uint2(0u, 0u);
-  float wix = 0.0f, wiy = 0.0f, wiz = 0.0f;  // world-space reciprocal direction (r is per-space)
-  uint32_t woct = 0;
   auto push = [&](uint2 e) {
     if (sp < KF_STACK) {
       stack[sp++] = e;
@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
   int spBlas = 0;
   auto popGroup = [&]() {
     if (inBlas && sp == spBlas) {
-      r.ox = o.x; r.oy = o.y; r.oz = o.z;
-      r.dx = d.x; r.dy = d.y; r.dz = d.z;
-      r.ix = wix; r.iy = wiy; r.iz = wiz;
-      r.octinv = woct;
+      r.ox = sWorld[0][tid]; r.oy = sWorld[1][tid]; r.oz = sWorld[2][tid];
+      r.dx = sWorld[3][tid]; r.dy = sWorld[4][tid]; r.dz = sWorld[5][tid];
+      r.ix = sWorld[6][tid]; r.iy = sWorld[7][tid]; r.iz = sWorld[8][tid];
+      r.octinv = __float_as_uint(sWorld[9][tid]);
       nodes = sc.tlasNodes;
       inBlas = false;
     }
@@ -132,16 +132,14 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
           if (qi < count) {
             slot = a.queue[qi];
             const float4 o4 = a.rayO[slot], d4 = a.rayD[slot];
-            o = mk3(o4.x, o4.y, o4.z);
-            d = mk3(d4.x, d4.y, d4.z);
+            const V3 o = mk3(o4.x, o4.y, o4.z);
+            const V3 d = mk3(d4.x, d4.y, d4.z);
             hit.t = ANY ? d4.w : 10000.0f;
             hit.u = hit.v = 0.0f;
             hit.inst = -1;
             hit.prim = -1;
             hit.front = 0;
             r = setupRay(o, d);
-            wix = r.ix; wiy = r.iy; wiz = r.iz;
-            woct = r.octinv;
             nodes = sc.tlasNodes;
             inBlas = false;
             nonOpaque = false;
@@ -188,6 +186,11 @@ __global__ void __launch_bounds__(128, KF_TRACE_MIN_BLOCKS) k_wf_trace(TraceArgs
           if (ng.y & 0xff000000u) push(ng);
           spBlas = sp;
           // world -> object (contract arithmetic, oracle traceInstance())
+          sWorld[0][tid] = r.ox; sWorld[1][tid] = r.oy; sWorld[2][tid] = r.oz;
+          sWorld[3][tid] = r.dx; sWorld[4][tid] = r.dy; sWorld[5][tid] = r.dz;
+          sWorld[6][tid] = r.ix; sWorld[7][tid] = r.iy; sWorld[8][tid] = r.iz;
+          sWorld[9][tid] = __uint_as_float(r.octinv);
+          const V3 o = mk3(r.ox, r.oy, r.oz), d = mk3(r.dx, r.dy, r.dz);
           V3 oo, od;
           oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
           oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
