@@ -27,6 +27,10 @@
 
 namespace kf {
 
+#ifndef KF_SHADE_MIN_BLOCKS
+#define KF_SHADE_MIN_BLOCKS 8
+#endif
+
 // Surface context spilled between light iterations (multi-light scenes only), 6 x float4.
 struct WfBuffers {
   float4* rayO;     // origin.xyz, -
@@ -163,7 +167,7 @@ KF_D void loadCtx(const float4* __restrict__ c, Surface& sf, int& k, V3& acc) {
 
 // ---------------------------------------------------------------------------------------------
 template <bool MULTI, bool DETAIL>
-__global__ void __launch_bounds__(128) k_wf_shade(WfArgs a, int q, uint32_t depth) {
+__global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a, int q, uint32_t depth) {
   const uint32_t count = a.b.counts[q];
   const uint32_t* __restrict__ queue = a.b.queue[q];
   const uint32_t stride = gridDim.x * blockDim.x;
