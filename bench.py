@@ -14,8 +14,9 @@ accumulate + encode epilogue -- strong scaling of one frame.
 
 `value` is timed on the device with everything resident in HBM; `e2e` is the same frame through the
 public facade call (Kuafu::run + downloadLatestFrame) with host buffers, H2D/D2H inside the timed
-region.  `--impl reference` times the CPU oracle (a C++ port of the reference's shaders; the reference's
-Vulkan-RT path cannot run on a B200) on the box's host cores.
+region.  `--impl reference` times the reference's own shaders compiled for the CPU (oracle/_ref, built from
+/root/reference by `make -C oracle ref`; the hand-written oracle port when that library is absent) on the
+box's host cores -- the reference's Vulkan-RT pipeline itself cannot run on a B200.
 """
 import argparse
 import json
@@ -161,8 +162,28 @@ def algorithmic_bytes(cnt, stats, n_pixels):
     return b, rays
 
 
+def cpu_arm():
+    """The CPU implementation that is timed beside the kernels: the reference's own shaders compiled for
+    the CPU (oracle/_ref/libkf_ref.so, built from /root/reference by `make -C oracle ref`; kind
+    "reference") when that library travelled with the snapshot, else the hand-written oracle port (kind
+    "port").  Both take traversal, triangle test and texture sampling from libkf_oracle.so."""
+    from oracle import oracle, ref
+    kind = "reference" if os.path.exists(ref._PATH) else "port"
+
+    def render(orc, cams, w, h, pc, sample_spp, clock, threads):
+        pcs = np.array(pc).copy()
+        pcs["sampleRatePerPixel"] = sample_spp
+        if kind == "reference":
+            out = ref.render(orc, cams, w, h, pcs, clock_base=clock, threads=threads)
+        else:
+            out = orc.render(cams, w, h, pcs, 0, sample_spp, clock_base=clock, threads=threads)
+        return out["counters"]["extensionRays"] + out["counters"]["shadowRays"]
+
+    return kind, render
+
+
 def run_reference(args, cfg, rank):
-    """CPU arm: the oracle (C++ port of the reference shaders) on all host cores, bounded sample."""
+    """CPU arm: the reference's shaders on all host cores (see cpu_arm), bounded sample."""
     if rank != 0:
         return
     from kuafu_b200 import host
@@ -176,12 +197,12 @@ def run_reference(args, cfg, rank):
     sample_spp = max(1, min(args.cpu_sample_spp, cfg["spp"]))
     cams = np.array(ws.cams[:1])
 
+    kind, cpu_render = cpu_arm()
+
     def step(i):
         t = time.perf_counter()
-        out = orc.render(cams, ws.w, ws.h, ws.pc, 0, sample_spp, clock_base=i * (cfg["spp"] + 1), threads=cores)
-        dt = time.perf_counter() - t
-        c = out["counters"]
-        return dt, c["extensionRays"] + c["shadowRays"]
+        rays = cpu_render(orc, cams, ws.w, ws.h, ws.pc, sample_spp, i * (cfg["spp"] + 1), cores)
+        return time.perf_counter() - t, rays
 
     for i in range(args.warmup):
         step(i)
@@ -200,7 +221,7 @@ def run_reference(args, cfg, rank):
         "ms_per_step": tot_t / args.steps * 1e3 * scale, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, **cfg},
-        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -396,11 +417,11 @@ def main():
         ws.upload(orc)
         cores = oracle.hardware_threads()
         sample_spp = max(1, min(args.cpu_sample_spp, spp))
+        kind, cpu_render = cpu_arm()
         t = time.perf_counter()
-        out = orc.render(cams, ws.w, ws.h, pc, 0, sample_spp, clock_base=0, threads=cores)
+        cr = cpu_render(orc, cams, ws.w, ws.h, pc, sample_spp, 0, cores)
         dt = time.perf_counter() - t
-        cr = out["counters"]["extensionRays"] + out["counters"]["shadowRays"]
-        cpu = {"value": cr / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+        cpu = {"value": cr / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
                "sample": f"{sample_spp} of {spp} spp of every pixel ({ws.w}x{ws.h}), one pass, {dt:.1f} s"}
 
     if rank == 0:

@@ -7,6 +7,8 @@ Outputs (git-ignored, but they travel to the GPU box with the snapshot):
     kuafu_b200/lib/libkfrt.so     CUDA core + C ABI (include/kf_rt.h), sm_100a
     kuafu_b200/lib/libkuafu.so    C++ host facade (kuafu.hpp API) + C shim, links libkfrt
     oracle/libkf_oracle.so        CPU oracle (test infrastructure only)
+    oracle/_ref/libkf_ref.so      the reference's shaders compiled for the CPU (test infrastructure only;
+                                  built only where /root/reference exists)
 """
 import os
 import shutil
@@ -83,10 +85,27 @@ def build_oracle(force=False):
     return out
 
 
+REFERENCE = os.environ.get("KUAFU_REFERENCE", "/root/reference")
+
+
+def build_ref(force=False):
+    """oracle/_ref/libkf_ref.so: the reference's shaders compiled for the CPU from where they lie (test
+    infrastructure).  Only where the reference tree exists; elsewhere the prebuilt file is used."""
+    d = os.path.join(ROOT, "oracle")
+    out = os.path.join(d, "_ref", "libkf_ref.so")
+    if not os.path.isdir(os.path.join(REFERENCE, "resources", "shaders")):
+        return out if os.path.exists(out) else None
+    if force and os.path.exists(out):
+        os.remove(out)
+    _run(["make", "-C", d, "ref", f"REFERENCE={REFERENCE}"])
+    return out
+
+
 def build_all(force=False, oracle=True):
     outs = [build_kfrt(force), build_host(force)]
     if oracle:
         outs.append(build_oracle(force))
+        outs.append(build_ref(force))
     return [o for o in outs if o]
 
 

@@ -178,6 +178,7 @@ struct SceneDev {
   const KfrtDirectionalLight* dl;
   const KfrtPointLights* pl;
   const KfrtActiveLights* al;
+  const float* alProjView;  // 16 floats per projector slot: proj * view, column major
   unsigned long long lightMask;  // bit k: light slot k (0 directional, 1..32 point, 33..40 active) is on
 };
 

@@ -121,6 +121,7 @@ struct KfrtContext {
   DevBuf<KfrtDirectionalLight> dl;
   DevBuf<KfrtPointLights> pl;
   DevBuf<KfrtActiveLights> al;
+  DevBuf<float> alProjView;  // proj * view of every projector slot (PathTrace.rchit:300: `proj * view * p`)
   uint32_t nLightSlots = 0;
   unsigned long long lightMask = 0;
   DevBuf<float> srgbToLinear, srgbThreshold;
@@ -494,7 +495,7 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
     thr[k] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
   }
   bool ok = ctx->srgbToLinear.ensure(256) == cudaSuccess && ctx->srgbThreshold.ensure(255) == cudaSuccess &&
-            ctx->dl.ensure(1) == cudaSuccess && ctx->pl.ensure(1) == cudaSuccess && ctx->al.ensure(1) == cudaSuccess &&
+            ctx->dl.ensure(1) == cudaSuccess && ctx->pl.ensure(1) == cudaSuccess && ctx->al.ensure(1) == cudaSuccess && ctx->alProjView.ensure(16 * KFRT_MAX_ACTIVE_LIGHTS) == cudaSuccess &&
             ctx->counters.ensure(16) == cudaSuccess;
   if (ok) {
     ok = cudaMemcpy(ctx->srgbToLinear.p, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -519,7 +520,7 @@ int kfrtDestroy(KfrtContext* ctx) {
   for (auto& g : ctx->geoms) g.freeAll();
   for (auto& t : ctx->texs) cudaFree(t.texels);
   ctx->geomTable.release(); ctx->blasInfo.release(); ctx->mats.release(); ctx->texTable.release();
-  ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release();
+  ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release(); ctx->alProjView.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
   ctx->instRec.release(); ctx->tlasNodes.release();
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
@@ -679,6 +680,23 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->dl.p, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->pl.p, &p, sizeof(p), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->al.p, &a, sizeof(a), cudaMemcpyHostToDevice, ctx->stream));
+  // GLSL evaluates `proj * view * vec4(worldPos, 1)` left to right: the matrix product comes first.
+  // Column j of proj * view is proj * (column j of view), each sum taken left to right; volatile keeps
+  // the host compiler from contracting the products into FMAs.
+  float pv[KFRT_MAX_ACTIVE_LIGHTS][16];
+  for (int i = 0; i < KFRT_MAX_ACTIVE_LIGHTS; i++)
+    for (int j = 0; j < 4; j++)
+      for (int r = 0; r < 4; r++) {
+        volatile float acc = a.projMat[i][r] * a.viewMat[i][4 * j + 0];
+        volatile float t1 = a.projMat[i][4 + r] * a.viewMat[i][4 * j + 1];
+        acc = acc + t1;
+        volatile float t2 = a.projMat[i][8 + r] * a.viewMat[i][4 * j + 2];
+        acc = acc + t2;
+        volatile float t3 = a.projMat[i][12 + r] * a.viewMat[i][4 * j + 3];
+        acc = acc + t3;
+        pv[i][4 * j + r] = acc;
+      }
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->alProjView.p, pv, sizeof(pv), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->nLightSlots = slots;
   return KFRT_OK;
@@ -1031,6 +1049,7 @@ static SceneDev sceneDev(KfrtContext* ctx) {
   sc.dl = ctx->dl.p;
   sc.pl = ctx->pl.p;
   sc.al = ctx->al.p;
+  sc.alProjView = ctx->alProjView.p;
   sc.lightMask = ctx->lightMask;
   return sc;
 }

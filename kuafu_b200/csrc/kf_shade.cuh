@@ -27,7 +27,9 @@ KF_D V3 getPerpendicularVector(V3 u) {
 KF_D float Schlick(float cosine, float ior) {
   float r0 = (1.0f - ior) / (1.0f + ior);
   r0 *= r0;
-  return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f);
+  // GLSL pow(x, y) is exp2(y * log2(x)) (Vulkan precision table: "inherited from exp2(y * log2(x))"),
+  // undefined for x < 0: the clamp makes that case 0 instead of NaN (same definition as the oracle)
+  return r0 + (1.0f - r0) * exp2f(5.0f * log2f(fmaxf(1.0f - cosine, 0.0f)));
 }
 KF_D float ggxNormalDistribution(float NdotH, float a2) {
   const float d = fmaxf(NdotH * NdotH * (a2 - 1) + 1, 1e-6f);
@@ -424,16 +426,14 @@ KF_D bool nextLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& 
       const int texID = int(sftp.z);
       V3 color = rgb;
       if (texID >= 0) {
-        const float* vm = sc.al->viewMat[i];
-        const float* pm = sc.al->projMat[i];
-        float vp[4], cp[4];
+        // proj * view * vec4(worldPos, 1) groups as (proj * view) * p; the product is made once in
+        // kfrtSetLights
+        const float* pv = sc.alProjView + 16 * i;
+        float cp[4];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-          vp[r] = ((__ldg(vm + r) * sf.worldPos.x + __ldg(vm + 4 + r) * sf.worldPos.y) + __ldg(vm + 8 + r) * sf.worldPos.z) +
-                  __ldg(vm + 12 + r) * 1.0f;
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-          cp[r] = ((__ldg(pm + r) * vp[0] + __ldg(pm + 4 + r) * vp[1]) + __ldg(pm + 8 + r) * vp[2]) + __ldg(pm + 12 + r) * vp[3];
+          cp[r] = ((__ldg(pv + r) * sf.worldPos.x + __ldg(pv + 4 + r) * sf.worldPos.y) + __ldg(pv + 8 + r) * sf.worldPos.z) +
+                  __ldg(pv + 12 + r) * 1.0f;
         const float tu = cp[0] / cp[3], tv = cp[1] / cp[3];
         color *= sampleTexture(sc, texID, tu * 0.5f + 0.5f, tv * 0.5f + 0.5f, texFetches);
       }

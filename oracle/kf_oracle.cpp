@@ -4,9 +4,19 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing in
 // kuafu_b200/ may include, link or call this file.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer values for this
-// path and its Vulkan-RT pipeline cannot be built or run here, so this
-// transcription *defines* the expected results.  Declared deviations from the reference:
+// PARITY PINNED against the reference's own shader code.  The reference ships no tests, golden
+// vectors or known-answer values for this path and its Vulkan-RT pipeline
+// cannot run here, but its shading code is plain GLSL: `make -C oracle ref` compiles
+// /root/reference/resources/shaders/PathTrace.{rgen,rchit,rahit,rmiss}, PathTraceShadow.rmiss and
+// base/*.glsl for the CPU from where they lie (ref_shim/glsl2cpp.py + glsl_shim.hpp +
+// kf_ref_host.cpp -> _ref/libkf_ref.so).  tests/test_cpu_ref_pin.py requires this restatement to
+// agree with those shaders BIT FOR BIT (image, albedo, normal, primary hit, ray counts) on seeded
+// scenes covering every light type, textures, environment map, emissive hits, transmission,
+// depth of field, Russian roulette, alpha-0 any-hit and frame accumulation, plus the five BASELINE
+// configs; tests/golden/ref_*.npz freezes the shaders' outputs for machines without the reference.
+// What stays outside the pin is what the reference itself delegates to driver and hardware --
+// acceleration-structure traversal, the triangle test, texture filtering, clockARB() -- which
+// shim and oracle share (kfo_trace, kfo_sample_*) and which the deviations below define:
 //   D1  clockARB() seeds (PathTrace.rgen:23,32) are replaced by a deterministic surrogate:
 //       pixel stream  = tea(pixel, clockBase), sample stream i = tea(pixel, clockBase + 1 + i).
 //   D2  triangle facing (gl_HitKindEXT) is "front <=> counter-clockwise seen from the ray origin in
@@ -16,7 +26,8 @@
 //       cube map is filtered inside one face with clamp-to-edge (hardware filters across seams).
 //   D5  the stochastic any-hit test for 0 < alpha < 1 (PathTrace.rahit:30-48) draws its random
 //       number from a hash of (ray.seed, instance, primitive) instead of advancing ray.seed in
-//       hardware traversal order, which is implementation-defined.
+//       hardware traversal order, which is implementation-defined (the shim runs the real
+//       PathTrace.rahit; the two agree statistically, tests/test_cpu_ref_pin.py).
 //
 // Arithmetic contract (shared with the CUDA kernels so that hit buffers can be bit-exact):
 // IEEE-754 binary32, round-to-nearest, NO fused multiply-add (compile with -ffp-contract=off),
@@ -113,7 +124,8 @@ static inline V3 getPerpendicularVector(V3 u) {  // Random.glsl:58-65
 static inline float Schlick(float cosine, float ior) {  // Random.glsl:68-73
   float r0 = (1.0f - ior) / (1.0f + ior);
   r0 *= r0;
-  return r0 + (1.0f - r0) * std::pow(1.0f - cosine, 5.0f);
+  // GLSL pow(x, y) = exp2(y * log2(x)) (Vulkan precision table), undefined for x < 0: clamped to 0
+  return r0 + (1.0f - r0) * std::exp2(5.0f * std::log2(std::fmax(1.0f - cosine, 0.0f)));
 }
 static inline float ggxNormalDistribution(float NdotH, float a2) {  // Random.glsl:75-79
   float d = std::fmax(NdotH * NdotH * (a2 - 1) + 1, 1e-6f);
@@ -363,6 +375,7 @@ struct Scene {
   float srgbToLinear[256];
   float srgbThreshold[255];  // linear value at which the 8-bit sRGB code becomes k+1
   bool accelDirty = true;
+  std::vector<const void*> viewVerts, viewIdx, viewMat;  // kfo_scene_view()
   Counters counters;
   std::string err;
 
@@ -510,9 +523,15 @@ static inline float hashRnd(uint32_t seed, uint32_t inst, uint32_t prim) {  // d
   return float(h & 0x00FFFFFFu) / float(0x01000000);
 }
 
+typedef int (*AnyHitFn)(void* user, int32_t inst, int32_t prim);  // 1 = accept the candidate
+
 struct Tracer {
   const Scene& s;
   bool brute;
+  // When set, candidates of non-opaque geometry are put to this callback instead of the D5 hash
+  // draw: oracle/ref_shim runs the reference's own PathTrace.rahit through it.
+  AnyHitFn anyHitFn = nullptr;
+  void* anyHitUser = nullptr;
   explicit Tracer(const Scene& sc, bool b) : s(sc), brute(b) {}
 
   // PathTrace.rahit:30-48 on a candidate of a non-opaque geometry.
@@ -533,7 +552,9 @@ struct Tracer {
                   (t == best.t && found &&
                    (int32_t(inst) < best.inst || (int32_t(inst) == best.inst && int32_t(prim) < best.prim)));
     if (!closer) return;
-    if (anyHit && !g.opaque && !anyHitAccepts(seed, inst, prim, g)) return;
+    if (anyHit && !g.opaque) {
+      if (anyHitFn ? !anyHitFn(anyHitUser, int32_t(inst), int32_t(prim)) : !anyHitAccepts(seed, inst, prim, g)) return;
+    }
     best = {t, u, v, int32_t(inst), int32_t(prim), det > 0.0f};
     found = true;
   }
@@ -865,9 +886,12 @@ struct Shader {
           int texID = int(s.al.sftp[i][2]);
           V3 color = rgb;
           if (texID >= 0) {
-            float vp[4], cp[4];
-            mulMat4(s.al.viewMat[i], worldPos.x, worldPos.y, worldPos.z, 1.0f, vp);
-            mulMat4(s.al.projMat[i], vp[0], vp[1], vp[2], vp[3], cp);  // proj * (view * p)
+            // `proj * view * vec4(worldPos, 1)` (rchit:300) is left-associative: (proj * view) * p
+            float pvm[16], cp[4];
+            for (int j = 0; j < 4; j++)
+              mulMat4(s.al.projMat[i], s.al.viewMat[i][4 * j], s.al.viewMat[i][4 * j + 1],
+                      s.al.viewMat[i][4 * j + 2], s.al.viewMat[i][4 * j + 3], pvm + 4 * j);
+            mulMat4(pvm, worldPos.x, worldPos.y, worldPos.z, 1.0f, cp);
             float tu = cp[0] / cp[3], tv = cp[1] / cp[3];
             float u = tu * 0.5f + 0.5f, v = tv * 0.5f + 0.5f;
             color *= sampleTexture(s, texID, u, v);
@@ -1288,6 +1312,86 @@ int kfo_resolve(void* h, const float* sum, float* rgba, uint8_t* bgra8, uint64_t
     }
   }
   return 0;
+}
+
+// ---- black boxes handed to oracle/ref_shim (the reference's shaders compiled for the CPU) ----------
+// The shim runs the reference's GLSL; what the GLSL delegates to the driver and the hardware --
+// traceRayEXT's traversal + triangle test, texture()'s sampler -- it takes from here, so that oracle
+// and shim share exactly these definitions and differ only in who wrote the shading code.
+struct KfoHitOut {
+  float t, u, v;
+  int32_t inst, prim, front;
+  float worldToObject[12];  // 3 rows x 4 columns
+};
+struct KfoSceneView {
+  uint32_t nGeoms, nMats, nInsts, nTex;
+  const void* const* verts;     // per geometry: 48-byte vertices
+  const void* const* idx;       // per geometry: uint32 indices
+  const void* const* matIndex;  // per geometry: uint32 material index per primitive
+  const void* mats;
+  const void* insts;
+  const void* dl;
+  const void* pl;
+  const void* al;
+  int32_t hasEnv;
+};
+
+int kfo_prepare(void* h) {
+  Scene& s = *static_cast<Scene*>(h);
+  if (s.accelDirty) buildAccel(s);
+  return 0;
+}
+
+int kfo_scene_view(void* h, KfoSceneView* v) {
+  Scene& s = *static_cast<Scene*>(h);
+  s.viewVerts.clear(); s.viewIdx.clear(); s.viewMat.clear();
+  for (const Geometry& g : s.geoms) {
+    s.viewVerts.push_back(g.verts.data());
+    s.viewIdx.push_back(g.idx.data());
+    s.viewMat.push_back(g.matIndex.data());
+  }
+  v->nGeoms = uint32_t(s.geoms.size());
+  v->nMats = uint32_t(s.mats.size());
+  v->nInsts = uint32_t(s.insts.size());
+  v->nTex = uint32_t(s.texs.size());
+  v->verts = s.viewVerts.data();
+  v->idx = s.viewIdx.data();
+  v->matIndex = s.viewMat.data();
+  v->mats = s.mats.data();
+  v->insts = s.insts.data();
+  v->dl = &s.dl;
+  v->pl = &s.pl;
+  v->al = &s.al;
+  v->hasEnv = s.hasEnv ? 1 : 0;
+  return 0;
+}
+
+// traceRayEXT's traversal: closest (or first, when terminateOnFirst) accepted hit with tmin < t < tmax.
+// anyHit != 0: candidates of non-opaque geometry go to `fn` (gl_RayFlagsOpaqueEXT clear).
+int kfo_trace(void* h, const float* o, const float* d, float tmin, float tmax, int anyHit, int terminateOnFirst,
+              int brute, AnyHitFn fn, void* user, KfoHitOut* out) {
+  const Scene& s = *static_cast<const Scene*>(h);
+  Tracer tr(s, brute != 0);
+  tr.anyHitFn = fn;
+  tr.anyHitUser = user;
+  Hit hit;
+  bool found = tr.trace(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), tmin, tmax, anyHit != 0, 0u,
+                        terminateOnFirst != 0, hit);
+  if (!found) return 0;
+  out->t = hit.t; out->u = hit.u; out->v = hit.v;
+  out->inst = hit.inst; out->prim = hit.prim; out->front = hit.front ? 1 : 0;
+  std::memcpy(out->worldToObject, s.instRt[hit.inst].inv, sizeof(out->worldToObject));
+  return 1;
+}
+
+void kfo_sample_texture(void* h, int32_t index, float u, float v, float* rgb) {
+  V3 c = sampleTexture(*static_cast<const Scene*>(h), index, u, v);
+  rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
+}
+
+void kfo_sample_cube(void* h, const float* dir, float* rgb) {
+  V3 c = sampleCube(*static_cast<const Scene*>(h), v3(dir[0], dir[1], dir[2]));
+  rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
 }
 
 int kfo_hardware_threads() { return int(std::thread::hardware_concurrency()); }
