@@ -140,7 +140,9 @@ typedef struct KfrtCounters {
   uint64_t shadowNodeVisits;     /* the occlusion-ray share of nodeVisits (detail) */
   uint64_t shadowTriangleTests;  /* the occlusion-ray share of triangleTests (detail) */
   uint64_t shadowInstanceVisits; /* the occlusion-ray share of instanceVisits (detail) */
-  uint64_t reserved[4];
+  uint64_t tlasNodeVisits;       /* the top-level share of nodeVisits, both ray kinds (detail) */
+  uint64_t instanceEntries;      /* instanceVisits whose world-box re-test passed: BLAS traversals (detail) */
+  uint64_t reserved[2];
 } KfrtCounters;
 
 /* BVH statistics for the roofline accounting in DESIGN.md. */

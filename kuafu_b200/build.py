@@ -17,7 +17,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "kuafu_b200")
-LIB = os.path.join(PKG, "lib")
+# KFRT_LIB_DIR: tooling hook for A/B runs of kernel variants (a directory holding both libraries)
+LIB = os.environ.get("KFRT_LIB_DIR") or os.path.join(PKG, "lib")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]

@@ -500,6 +500,7 @@ KF_D void quantiseNode(Node8& nd, const Box6& nbIn, const Box6* slotBox, uint32_
 
 #define KF_MEMBER_EMPTY 0x7fffffff
 #define KF_LEAF_MAX 2
+static_assert(KF_LEAF_MAX <= 2, "Node8::triMask holds two bits per leaf slot");
 
 struct CollapseArgs {
   int n;                      // primitives
@@ -525,10 +526,10 @@ KF_D int memberFirst(int code, const int2* __restrict__ range) { return code < 0
 
 // One thread per wide node of the current level [lo, hi).
 //
-// TLAS == false (bottom level): leaves hold up to KF_LEAF_MAX triangles; meta/primBase as documented
-// at Node8.
+// TLAS == false (bottom level): leaves hold up to KF_LEAF_MAX triangles; triMask/primBase as
+// documented at Node8.
 // TLAS == true (top level): every child is addressed like an internal child (imask = present mask,
-// meta = 0x20 | 24 + slot, children consecutive from childBase in slot order) and is either a real
+// no triangle fields, children consecutive from childBase in slot order) and is either a real
 // node or an InstNode record; primBase holds the mask of the slots that are real nodes.  Instances
 // thereby take part in the octant-ordered front-to-back traversal instead of being entered in
 // storage order.
@@ -611,34 +612,34 @@ __global__ void k_collapse_level(CollapseArgs a, uint32_t lo, uint32_t hi) {
   Node8 nd;
   nd.childBase = childBase;
   nd.primBase = primBase;
-  uint32_t imask = 0, ci = 0, po = 0, realNodes = 0;
+  uint32_t imask = 0, ci = 0, po = 0, realNodes = 0, triMask = 0;
   for (int s = 0; s < 8; s++) {
     const int code = slotMem[s];
     a.wideMembers[8 * w + s] = code;
-    if (code == KF_MEMBER_EMPTY) { nd.meta[s] = 0; continue; }
+    if (code == KF_MEMBER_EMPTY) continue;
     const int cnt = memberCount(code, a.range);
     if (cnt > LEAF_MAX) {
       imask |= 1u << s;
       realNodes |= 1u << s;
-      nd.meta[s] = uint8_t(0x20u | (24u + s));
       a.wideBinary[childBase + ci] = code;
       ci++;
     } else if (TLAS) {
       const uint32_t prim = a.vals[memberFirst(code, a.range)];
       imask |= 1u << s;
-      nd.meta[s] = uint8_t(0x20u | (24u + s));
       a.wideBinary[childBase + ci] = ~int(prim);
       a.slotOfInst[prim] = childBase + ci;
       ci++;
     } else {
       const int first = memberFirst(code, a.range);
-      nd.meta[s] = uint8_t((((1u << cnt) - 1u) << 5) | po);
+      triMask |= ((1u << cnt) - 1u) << (2 * s);
       for (int q = 0; q < cnt; q++) a.outPrim[primBase + po + q] = a.vals[first + q];
       po += cnt;
     }
   }
   if (TLAS) nd.primBase = realNodes;
   nd.imask = uint8_t(imask);
+  nd.triMask = triMask * 0x00010001u;
+  nd.reserved = 0;
   quantiseNode(nd, nb, slotBox, used);
   a.outNodes[w] = nd;
 }
@@ -655,8 +656,9 @@ __global__ void k_single_leaf_root(int n, const float* __restrict__ primBox, Nod
   nd.primBase = 0;
   nd.imask = 0;
   Box6 slotBox[8];
-  for (int s = 0; s < 8; s++) { nd.meta[s] = 0; wideMembers[s] = KF_MEMBER_EMPTY; }
-  nd.meta[0] = uint8_t((((1u << n) - 1u) << 5) | 0u);
+  for (int s = 0; s < 8; s++) wideMembers[s] = KF_MEMBER_EMPTY;
+  nd.triMask = ((1u << n) - 1u) * 0x00010001u;
+  nd.reserved = 0;
   slotBox[0] = nb;
   for (int i = 0; i < n; i++) outPrim[i] = uint32_t(i);
   quantiseNode(nd, nb, slotBox, 1u);
@@ -674,8 +676,9 @@ __global__ void k_single_instance_root(const float* __restrict__ primBox, Node8*
   nd.primBase = 0;  // no real-node children
   nd.imask = 1;
   Box6 slotBox[8];
-  for (int s = 0; s < 8; s++) { nd.meta[s] = 0; wideMembers[s] = KF_MEMBER_EMPTY; wideMembers[8 + s] = KF_MEMBER_EMPTY; }
-  nd.meta[0] = uint8_t(0x20u | 24u);
+  for (int s = 0; s < 8; s++) { wideMembers[s] = KF_MEMBER_EMPTY; wideMembers[8 + s] = KF_MEMBER_EMPTY; }
+  nd.triMask = 0;
+  nd.reserved = 0;
   slotBox[0] = nb;
   quantiseNode(nd, nb, slotBox, 1u);
   outNodes[0] = nd;

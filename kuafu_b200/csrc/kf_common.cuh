@@ -110,7 +110,12 @@ struct __align__(16) Node8 {
   uint8_t ex, ey, ez, imask;  // imask bit i: child slot i is an internal node
   uint32_t childBase;         // index of first internal child (children are consecutive by slot)
   uint32_t primBase;          // index of first leaf primitive (triangle / instance-list entry)
-  uint8_t meta[8];            // 0 empty | internal: 0x20|(24+slot) | leaf: unary(count)<<5 | offset
+  // Leaf children: slot s owns the two-bit field 2s..2s+1 of a 16-bit triangle mask (unary count of
+  // its triangles, at most 2 per leaf); the triangles of a node lie compactly from primBase in slot
+  // order, so the triangle of mask bit b is primBase + popc(mask below b).  The mask is stored in
+  // both halves of triMask (low half: ANDed with the expanded hit mask, high half: kept as is).
+  uint32_t triMask;
+  uint32_t reserved;
   uint8_t qlox[8], qloy[8], qloz[8];
   uint8_t qhix[8], qhiy[8], qhiz[8];
 };

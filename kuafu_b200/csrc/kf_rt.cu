@@ -1237,6 +1237,8 @@ int kfrtGetCounters(KfrtContext* ctx, KfrtCounters* out) {
   out->shadowTriangleTests = h[9];
   out->shadowInstanceVisits = h[10];
   out->textureFetches = h[7];
+  out->tlasNodeVisits = h[12];
+  out->instanceEntries = h[13];
   out->kernelLaunches = ctx->launches;
   return KFRT_OK;
 }

@@ -67,15 +67,19 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   const uint32_t laneLt = (1u << lane) - 1u;
   const float tmin = 0.001f;
 
-  TravCounters tc{0, 0, 0};
+  TravCounters tc{0, 0, 0, 0, 0};
   uint2 stack[KF_STACK];
   int sp = 0;
   bool active = false, exhausted = false;
   uint32_t slot = 0;
   RaySetup r = setupRay(mk3(0.0f), mk3(1.0f));
-  // The world-space ray setup waits in shared memory while the lane is inside a bottom-level
-  // structure (r then holds the object-space ray): ten registers less per lane.
+  // The world-space ray setup waits in shared memory (written once, when the ray is fetched) while
+  // the lane is inside a bottom-level structure (r then holds the object-space ray): ten registers
+  // less per lane.
   __shared__ float sWorld[10][128];
+  __shared__ MaskTables sMask;
+  fillMaskTables(sMask);
+  __syncthreads();
   const uint32_t tid = threadIdx.x;
   Hit hit;
   hit.t = 0.0f; hit.u = hit.v = 0.0f; hit.inst = hit.prim = -1; hit.front = 0;
@@ -140,6 +144,11 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
             hit.prim = -1;
             hit.front = 0;
             r = setupRay(o, d);
+            // the world-space setup is parked once per ray; popGroup() restores it on every return
+            sWorld[0][tid] = r.ox; sWorld[1][tid] = r.oy; sWorld[2][tid] = r.oz;
+            sWorld[3][tid] = r.dx; sWorld[4][tid] = r.dy; sWorld[5][tid] = r.dz;
+            sWorld[6][tid] = r.ix; sWorld[7][tid] = r.iy; sWorld[8][tid] = r.iz;
+            sWorld[9][tid] = __uint_as_float(r.octinv);
             nodes = sc.tlasNodes;
             inBlas = false;
             nonOpaque = false;
@@ -183,13 +192,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
           const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);
           // what is left of this top-level node waits on the stack, below the bottom-level entries
+          if (DETAIL) tc.entries++;
           if (ng.y & 0xff000000u) push(ng);
           spBlas = sp;
           // world -> object (contract arithmetic, oracle traceInstance())
-          sWorld[0][tid] = r.ox; sWorld[1][tid] = r.oy; sWorld[2][tid] = r.oz;
-          sWorld[3][tid] = r.dx; sWorld[4][tid] = r.dy; sWorld[5][tid] = r.dz;
-          sWorld[6][tid] = r.ix; sWorld[7][tid] = r.iy; sWorld[8][tid] = r.iz;
-          sWorld[9][tid] = __uint_as_float(r.octinv);
           const V3 o = mk3(r.ox, r.oy, r.oz), d = mk3(r.dx, r.dy, r.dz);
           V3 oo, od;
           oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     }
 
     // ---- node phase: lanes without pending triangles take one node step -------------------------
-    if (active && tg.y == 0u && (ng.y & 0xff000000u)) {
+    if (active && !(tg.y & 0xffffu) && (ng.y & 0xff000000u)) {
       const uint32_t hits = ng.y;
       const int p = 31 - __clz(hits);
       const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;
@@ -218,19 +224,21 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
         ng.y &= ~(1u << p);
         if (ng.y & 0xff000000u) push(ng);
         const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
-        uint32_t childBase, primBase, imask;
-        const uint32_t hm = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask);
+        uint32_t childBase, primBase, imask, triMask;
+        const uint32_t miss = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask, triMask);
         if (DETAIL) tc.nodes++;
-        // top level: imask = present children, primBase = which of them are real nodes
-        ng = make_uint2(childBase, (hm & 0xff000000u) | imask | (inBlas ? 0u : (primBase & 0xffu) << 8));
-        tg = make_uint2(primBase, inBlas ? (hm & 0x00ffffffu) : 0u);
+        if (DETAIL && !inBlas) tc.tlasNodes++;
+        const uint32_t inner = sMask.perm[r.octinv][imask & ~miss];
+        // top level: imask = present children, primBase = which of them are real nodes (triMask = 0)
+        ng = make_uint2(childBase, (inner << 24) | imask | (inBlas ? 0u : (primBase & 0xffu) << 8));
+        tg = make_uint2(primBase, (uint32_t(sMask.expand[miss]) | 0xffff0000u) & triMask);
       }
     }
     // ---- triangle phase (bottom level): one leaf triangle per lane -------------------------------
-    if (active && !finished && tg.y != 0u) {
+    if (active && !finished && (tg.y & 0xffffu)) {
       const int b = __ffs(tg.y) - 1;
       tg.y &= tg.y - 1;
-      const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + b);
+      const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + __popc((tg.y >> 16) & ((1u << b) - 1u)));
       const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
       if (DETAIL) tc.tris++;
       // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
       }
     }
     // ---- pop: lanes with nothing left in hand take the next group from their stack ----------------
-    if (active && !finished && tg.y == 0u && !(ng.y & 0xff000000u)) popGroup();
+    if (active && !finished && !(tg.y & 0xffffu) && !(ng.y & 0xff000000u)) popGroup();
 
     if (finished) {
       if (ANY) {
@@ -283,6 +291,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     atomicAdd(a.counters + a.detailBase + 0, (unsigned long long)tc.nodes);
     atomicAdd(a.counters + a.detailBase + 1, (unsigned long long)tc.tris);
     atomicAdd(a.counters + a.detailBase + 2, (unsigned long long)tc.insts);
+    atomicAdd(a.counters + 12, (unsigned long long)tc.tlasNodes);
+    atomicAdd(a.counters + 13, (unsigned long long)tc.entries);
   }
 }
 

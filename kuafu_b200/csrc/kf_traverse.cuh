@@ -2,12 +2,14 @@
 // setup, the 8-box slab test of one node); the traversal loop itself is the persistent kernel in
 // kf_trace.cuh.
 //
-// Traversal state is a small stack of 8-byte "groups":
+// Traversal state:
 //   node group      (childBase, hits<<24 | kind<<8 | mask) -- children still to visit, in octant
 //                    priority order (highest bit first); mask = internal children (bottom level) or
-//                    present children (top level, where kind marks the real nodes among them)
-//   primitive group (primBase, 24-bit mask)                -- leaf triangles (bottom level)
-//   sentinel        (x, 0)                                 -- marks the return to the top level
+//                    present children (top level, where kind marks the real nodes among them);
+//                    node groups wait on the lane's stack
+//   triangle group  (primBase, triMask<<16 | hits)         -- leaf triangles of the last node step
+//                    (bottom level, never stacked): bit b of hits is triangle
+//                    primBase + popc(triMask below b)
 #pragma once
 
 #include "kf_common.cuh"
@@ -17,7 +19,7 @@ namespace kf {
 #define KF_STACK 48
 
 struct TravCounters {
-  uint32_t nodes, tris, insts;
+  uint32_t nodes, tris, insts, tlasNodes, entries;
 };
 
 struct RaySetup {
@@ -56,10 +58,37 @@ KF_D float planeFloat(uint32_t w, int j) {
   return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3200u | (uint32_t(4 + j) << 4)));
 }
 
-// Intersects the 8 quantised child boxes of `node`; returns the CWBVH hit mask:
-// bits 24..31 internal children by traversal priority, bits 0..23 leaf primitives.
+// Hit-mask tables (shared memory, filled by every block of the traversal kernel).  The slab test
+// yields one *miss* bit per child slot; what the traversal needs is
+//   internal children by traversal priority: slot s at bit s ^ octinv   -> perm[octinv][hit slots]
+//   leaf triangles: the two-bit field of every hit slot                 -> expand[missed slots]
+// Built arithmetically that costs ~50 ALU-pipe instructions per node (byte extraction, variable
+// shifts, selects): the ALU pipe is the busiest unit of this kernel (ncu: 66 % active against 28 % for
+// the FMA pipe), the load/store path has room, so two table lookups replace them.
+struct MaskTables {
+  uint8_t perm[8][256];
+  uint16_t expand[256];
+};
+KF_D void fillMaskTables(MaskTables& t) {
+  for (uint32_t i = threadIdx.x; i < 8u * 256u; i += blockDim.x) {
+    const uint32_t o = i >> 8, h = i & 0xffu;
+    uint32_t m = 0;
+    for (uint32_t s = 0; s < 8; s++)
+      if ((h >> s) & 1u) m |= 1u << (s ^ o);
+    t.perm[o][h] = uint8_t(m);
+  }
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+    uint32_t m = 0;
+    for (uint32_t s = 0; s < 8; s++)
+      if (!((i >> s) & 1u)) m |= 3u << (2 * s);
+    t.expand[i] = uint16_t(m);
+  }
+}
+
+// Slab-tests the 8 quantised child boxes of `node`; returns the mask of the child slots the ray
+// MISSES (bit s = slot s; empty slots may report either, the caller masks with imask / triMask).
 KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, float tmin, float tmax,
-                            uint32_t& childBase, uint32_t& primBase, uint32_t& imask) {
+                            uint32_t& childBase, uint32_t& primBase, uint32_t& imask, uint32_t& triMask) {
   const uint4* q = reinterpret_cast<const uint4*>(node);
   const uint4 n0 = __ldg(q + 0);
   const uint4 n1 = __ldg(q + 1);
@@ -68,6 +97,7 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
   const uint4 n4 = __ldg(q + 4);
   childBase = n1.x;
   primBase = n1.y;
+  triMask = n1.z;
   imask = n0.w >> 24;
   // per-axis grid step 2^(e-127), pre-multiplied by 2^15 (see planeFloat)
   const float sx = __uint_as_float(((n0.w & 0xffu) + 15u) << 23);
@@ -81,21 +111,13 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
   const bool nx = r.ix < 0.0f, ny = r.iy < 0.0f, nz = r.iz < 0.0f;
   const uint32_t lox[2] = {n2.x, n2.y}, loy[2] = {n2.z, n2.w}, loz[2] = {n3.x, n3.y};
   const uint32_t hix[2] = {n3.z, n3.w}, hiy[2] = {n4.x, n4.y}, hiz[2] = {n4.z, n4.w};
-  const uint32_t meta[2] = {n1.z, n1.w};
-  const uint32_t octinv4 = r.octinv * 0x01010101u;
-  uint32_t hitmask = 0;
+  uint32_t miss = 0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const uint32_t nearx = nx ? hix[h] : lox[h], farx = nx ? lox[h] : hix[h];
     const uint32_t neary = ny ? hiy[h] : loy[h], fary = ny ? loy[h] : hiy[h];
     const uint32_t nearz = nz ? hiz[h] : loz[h], farz = nz ? loz[h] : hiz[h];
-    // four children at a time: where does a hit go in the mask, and which bits does it set?
-    // internal children (meta = 0x20 | 24 + slot) land on bit 24 + (slot ^ octinv), i.e. in traversal
-    // priority order; leaves set `unary count` bits from their offset; empty slots (meta 0) set none.
-    const uint32_t meta4 = meta[h];
-    const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4;  // 1 per internal child
-    const uint32_t index4 = (meta4 ^ (octinv4 & (inner4 * 0xffu))) & 0x1f1f1f1fu;
-    const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
+    uint32_t sgn[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const float t0x = fmaf(planeFloat(nearx, j), ax, bx);
@@ -104,13 +126,20 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
       const float t1x = fmaf(planeFloat(farx, j), ax, bx);
       const float t1y = fmaf(planeFloat(fary, j), ay, by);
       const float t1z = fmaf(planeFloat(farz, j), az, bz);
-      const float t0 = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-      const float t1 = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      const uint32_t bits = __byte_perm(bits4, 0u, 0x4440u | uint32_t(j)), index = __byte_perm(index4, 0u, 0x4440u | uint32_t(j));
-      hitmask |= (t0 <= t1) ? (bits << index) : 0u;
+      const float t0 = fmaxf(fmaxf(t0x, t0y), t0z);
+      const float t1 = fminf(fminf(t1x, t1y), t1z);
+      // max(t0, tmin) <= min(t1, tmax)  <=>  none of these three differences is negative.  The
+      // subtractions run on the FMA pipe and the verdict is a sign bit (t1 is never NaN and a
+      // difference of equal values is +0; inf - inf gives the positive default NaN: a spurious hit,
+      // never a lost one).
+      sgn[j] = __float_as_uint(t1 - t0) | __float_as_uint(t1 - tmin) | __float_as_uint(tmax - t0);
     }
+    // sign bytes of the four children -> one nibble
+    const uint32_t x = __byte_perm(sgn[0], sgn[1], 0x7373u), y = __byte_perm(sgn[2], sgn[3], 0x7373u);
+    const uint32_t z = __byte_perm(x, y, 0x5410u) & 0x80808080u;
+    miss |= ((z * 0x00204081u) >> 28) << (4 * h);
   }
-  return hitmask;
+  return miss;
 }
 
 // Order-independent surrogate of the stochastic any-hit draw (reference PathTrace.rahit:30-48;

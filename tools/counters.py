@@ -23,6 +23,7 @@ sn, st, si = int(c["shadowNodeVisits"]), int(c["shadowTriangleTests"]), int(c["s
 n, t, i = int(c["nodeVisits"]) - sn, int(c["triangleTests"]) - st, int(c["instanceVisits"]) - si
 print(f"{scene}: paths {int(c['paths'])}, extension rays {ext} ({int(c['extensionHits'])/max(ext,1):.2f} hit), shadow rays {sh}")
 print(f"  closest-hit per ray: nodes {n/max(ext,1):.2f} tris {t/max(ext,1):.2f} instances {i/max(ext,1):.2f}")
+print(f"  both kinds  per ray: top-level nodes {int(c['tlasNodeVisits'])/max(ext+sh,1):.2f}, instance entries {int(c['instanceEntries'])/max(ext+sh,1):.2f} of {(i+si)/max(ext+sh,1):.2f} visits")
 print(f"  occlusion   per ray: nodes {sn/max(sh,1):.2f} tris {st/max(sh,1):.2f} instances {si/max(sh,1):.2f}")
 ts = []
 ctx.set_stage_timers(True)
