@@ -150,6 +150,7 @@ struct KfrtContext {
   int numSMs = 148;
   size_t batchSlotTarget = size_t(32) << 20;
   int refillIdle = KF_REFILL_IDLE;
+  bool traceLog = false;  // KFRT_TRACE_LOG=1: per-launch ray count and time of every traversal stage on stderr
   size_t wfSlots = 0;
   bool wfMulti = false;
   DevBuf<float4> wfRayO, wfRayD, wfHitA, wfStateW, wfStateC, wfShadowL, wfShadowC, wfCtx;
@@ -480,6 +481,7 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
   ctx->stream = ctx->ownStream;
   ctx->numSMs = prop.multiProcessorCount;
   if (const char* e = std::getenv("KFRT_REFILL_IDLE")) ctx->refillIdle = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
     if (v > 0) ctx->batchSlotTarget = size_t(v);
@@ -933,6 +935,20 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   const int d = ctx->detail ? 1 : 0;
   const int variant = (multi ? 2 : 0) + d;
   cudaStream_t st = ctx->stream;
+  // debugging aid (KFRT_TRACE_LOG): synchronous per-launch timing of the traversal stages
+  cudaEvent_t logEv[2] = {nullptr, nullptr};
+  if (ctx->traceLog) { cudaEventCreate(&logEv[0]); cudaEventCreate(&logEv[1]); }
+  auto logBegin = [&]() { if (ctx->traceLog) cudaEventRecord(logEv[0], st); };
+  auto logEnd = [&](const char* what, uint32_t depth, const uint32_t* countDev) {
+    if (!ctx->traceLog) return;
+    cudaEventRecord(logEv[1], st);
+    cudaEventSynchronize(logEv[1]);
+    float ms = 0.0f;
+    uint32_t n = 0;
+    cudaEventElapsedTime(&ms, logEv[0], logEv[1]);
+    cudaMemcpy(&n, countDev, sizeof(n), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[kfrt] %s depth %u: %u rays, %.3f ms, %.1f Mrays/s\n", what, depth, n, ms, n / (ms * 1e3 + 1e-9));
+  };
   for (uint32_t b0 = ra.s0; b0 < ra.s1; b0 += batch) {
     a.batchBegin = b0;
     a.batchCount = std::min(batch, ra.s1 - b0);
@@ -961,8 +977,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.detailBase = 4;
       te.refillIdle = ctx->refillIdle;
       stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
+      logBegin();
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
       else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
+      logEnd("closest", depth, te.count);
       stageMark(ctx, KFRT_STAGE_SHADE);
       switch (variant) {
         case 0: k_wf_shade<false, false><<<ctx->gridShade[0], 128, 0, st>>>(a, q, depth); break;
@@ -983,8 +1001,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
         ts.rayCounter = 2;
         ts.detailBase = 8;
         stageMark(ctx, KFRT_STAGE_TRACE_OCCLUSION);
+        logBegin();
         if (d) k_wf_trace<true, true><<<ctx->gridTrace[3], 128, 0, st>>>(ts);
         else k_wf_trace<true, false><<<ctx->gridTrace[2], 128, 0, st>>>(ts);
+        logEnd("occlusion", depth, ts.count);
         stageMark(ctx, KFRT_STAGE_SHADOW_RESOLVE);
         switch (variant) {
           case 0: k_wf_shadow_resolve<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
@@ -1005,6 +1025,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     ctx->launches++;
   }
   stageMark(ctx, KFRT_STAGE_END);
+  if (ctx->traceLog) { cudaEventDestroy(logEv[0]); cudaEventDestroy(logEv[1]); }
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }

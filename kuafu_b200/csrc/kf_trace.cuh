@@ -28,6 +28,9 @@
 
 namespace kf {
 
+#ifndef KF_STACK_SHARED
+#define KF_STACK_SHARED 8  // stack entries per lane kept in shared memory (8 KB per block)
+#endif
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
 
 struct TraceArgs {
@@ -90,13 +93,19 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
 
   bool finished = false;
-  // The stack lives in local memory with its top entry mirrored in registers: a pop hands out the
-  // register copy at once and issues the load of the entry below it, whose latency is then hidden
-  // behind the node step that follows.
+  // The first KF_STACK_SHARED entries of the stack live in shared memory, deeper ones (rare) in local
+  // memory, and the top entry is mirrored in registers: a pop hands out the register copy at once
+  // and reads the entry below it.  (ncu, all-local version: the reload of the entry below was the
+  // largest single long-scoreboard stall of the kernel, 6.4 % of all samples, and the stack lines
+  // competed with the BVH for L1.)
+  __shared__ uint2 sStack[KF_STACK_SHARED][128];
   uint2 top = make_uint2(0u, 0u);
   auto push = [&](uint2 e) {
-    if (sp < KF_STACK) {
-      stack[sp++] = e;
+    if (sp < KF_STACK_SHARED) {
+      sStack[sp++][tid] = e;
+      top = e;
+    } else if (sp < KF_STACK_SHARED + KF_STACK) {
+      stack[sp++ - KF_STACK_SHARED] = e;
       top = e;
     }
   };
@@ -119,7 +128,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     }
     ng = top;
     --sp;
-    if (sp > 0) top = stack[sp - 1];
+    if (sp > KF_STACK_SHARED) top = stack[sp - 1 - KF_STACK_SHARED];
+    else if (sp > 0) top = sStack[sp - 1][tid];
   };
 
   for (;;) {
