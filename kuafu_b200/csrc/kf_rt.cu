@@ -129,6 +129,7 @@ struct KfrtContext {
   std::vector<KfrtInstance> instHost;
   DevBuf<KfrtInstance> instDev;
   DevBuf<InstRec> instRec;
+  DevBuf<int> instBoxInt;  // per-instance world boxes as ordered ints (k_instance_box)
   DevBuf<Node8> tlasNodes;
   uint32_t nTlasNodes = 0;
   bool blasBuilt = false, tlasBuilt = false;
@@ -226,16 +227,38 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
 // st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
 // tlas: top-level layout -- every instance becomes an InstNode slot inside outNodes (st.slotOfInst),
 // so the array holds up to n real nodes plus n instance slots.
-static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
-  st.n = n;
+// Scratch of a build over n primitives (DevBuf::ensure only ever grows a buffer).
+static int reserveBuild(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
   const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
+  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
+  KF_CUDA(ctx, st.sceneBox.ensure(6));
   KF_CUDA(ctx, st.outNodes.ensure(maxNodes));
   KF_CUDA(ctx, st.outPrim.ensure(n));
   KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * maxNodes));
   KF_CUDA(ctx, st.wideBinary.ensure(maxNodes));
-  KF_CUDA(ctx, st.counters.ensure(2));
+  KF_CUDA(ctx, st.counters.ensure(4));
   KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
   if (tlas) KF_CUDA(ctx, st.slotOfInst.ensure(std::max<uint32_t>(n, 1)));
+  if ((tlas && n == 1) || (!tlas && n <= KF_LEAF_MAX)) return KFRT_OK;
+  KF_CUDA(ctx, st.hist.ensure(size_t(256) * gridFor(n, KF_SORT_TILE)));
+  KF_CUDA(ctx, st.keysA.ensure(n));
+  KF_CUDA(ctx, st.keysB.ensure(n));
+  KF_CUDA(ctx, st.valsA.ensure(n));
+  KF_CUDA(ctx, st.valsB.ensure(n));
+  KF_CUDA(ctx, st.children.ensure(n));
+  KF_CUDA(ctx, st.range.ensure(n));
+  KF_CUDA(ctx, st.parent.ensure(size_t(2) * n));
+  KF_CUDA(ctx, st.flags.ensure(n));
+  return KFRT_OK;
+}
+
+static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
+  st.n = n;
+  const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
+  {
+    int rc = reserveBuild(ctx, st, n, tlas);
+    if (rc) return rc;
+  }
   if (tlas && n == 1) {
     k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, st.outNodes.p, st.wideBinary.p,
                                                       st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
@@ -250,14 +273,6 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     KF_CUDA(ctx, cudaGetLastError());
     return KFRT_OK;
   }
-  KF_CUDA(ctx, st.keysA.ensure(n));
-  KF_CUDA(ctx, st.keysB.ensure(n));
-  KF_CUDA(ctx, st.valsA.ensure(n));
-  KF_CUDA(ctx, st.valsB.ensure(n));
-  KF_CUDA(ctx, st.children.ensure(n));
-  KF_CUDA(ctx, st.range.ensure(n));
-  KF_CUDA(ctx, st.parent.ensure(size_t(2) * n));
-  KF_CUDA(ctx, st.flags.ensure(n));
   k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
   int rc = radixSort(ctx, st, n);
   if (rc) return rc;
@@ -266,8 +281,9 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
   KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
   k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
                                                           st.sortedVals, st.nodeBox.p, st.flags.p);
-  // collapse, one launch per level of the wide tree
-  const uint32_t init[2] = {1u, 0u};
+  // collapse, one launch per level of the wide tree; the level ranges stay on the device and the
+  // host looks at them once per batch of launches
+  const uint32_t init[4] = {1u, 0u, 0u, 1u};
   const int zero = 0;
   KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(st.wideBinary.p, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -284,17 +300,22 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
   a.wideMembers = st.wideMembers.p;
   a.counters = st.counters.p;
   a.slotOfInst = tlas ? st.slotOfInst.p : nullptr;
-  uint32_t lo = 0, hi = 1;
-  while (lo < hi) {
-    if (tlas) k_collapse_level<true><<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
-    else k_collapse_level<false><<<gridFor(hi - lo, 64), 64, 0, ctx->stream>>>(a, lo, hi);
-    uint32_t cnt = 0;
-    KF_CUDA(ctx, cudaMemcpyAsync(&cnt, st.counters.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  const unsigned grid = std::min<unsigned>(gridFor(maxNodes, 64), unsigned(ctx->numSMs) * 16u);
+  uint32_t lv[4] = {0, 0, 0, 1};
+  // a balanced 8-wide tree over n / 2 leaves has log8(n / 2) levels; LBVH trees are a little deeper
+  int levels = 4;
+  for (uint32_t m = n; m > 16; m >>= 3) levels++;
+  while (lv[2] < lv[3]) {
+    for (int level = 0; level < levels; level++) {
+      if (tlas) k_collapse_level<true><<<grid, 64, 0, ctx->stream>>>(a);
+      else k_collapse_level<false><<<grid, 64, 0, ctx->stream>>>(a);
+      k_next_level<<<1, 1, 0, ctx->stream>>>(st.counters.p);
+    }
+    KF_CUDA(ctx, cudaMemcpyAsync(lv, st.counters.p, sizeof(lv), cudaMemcpyDeviceToHost, ctx->stream));
     KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    lo = hi;
-    hi = cnt;
-    if (hi > maxNodes) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
+    if (lv[0] > maxNodes) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
   }
+  const uint32_t hi = lv[0];
   st.nWide = hi;
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
@@ -309,8 +330,9 @@ static void orderedBoxToFloat(const int* ib, float* out) {
 }
 
 static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
-  cudaFree(g.nodes);
-  cudaFree(g.tris);
+  // nodes / triangles come from the stream-ordered pool: no device-wide synchronisation per BLAS
+  if (g.nodes) cudaFreeAsync(g.nodes, ctx->stream);
+  if (g.tris) cudaFreeAsync(g.tris, ctx->stream);
   g.nodes = nullptr;
   g.tris = nullptr;
   g.nNodes = 0;
@@ -321,16 +343,17 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   KF_CUDA(ctx, st.sceneBox.ensure(6));
   k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
   k_tri_boxes<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, nTris, st.primBox.p, st.sceneBox.p);
+  // the geometry's box travels with the synchronisation the collapse loop needs anyway
+  int ib[6];
+  KF_CUDA(ctx, cudaMemcpyAsync(ib, st.sceneBox.p, sizeof(ib), cudaMemcpyDeviceToHost, ctx->stream));
   int rc = buildWideBvh(ctx, st, nTris, false);
   if (rc) return rc;
-  KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.nodes), sizeof(Node8) * st.nWide));
-  KF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris));
+  if (nTris <= KF_LEAF_MAX) KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.nodes), sizeof(Node8) * st.nWide, ctx->stream));
+  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(g.nodes, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice,
                                ctx->stream));
   k_write_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, st.outPrim.p, nTris, g.tris);
-  int ib[6];
-  KF_CUDA(ctx, cudaMemcpyAsync(ib, st.sceneBox.p, sizeof(ib), cudaMemcpyDeviceToHost, ctx->stream));
-  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   orderedBoxToFloat(ib, g.box);
   g.nNodes = st.nWide;
   return KFRT_OK;
@@ -480,6 +503,13 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
   }
   ctx->stream = ctx->ownStream;
   ctx->numSMs = prop.multiProcessorCount;
+  {  // BLAS storage comes from the stream-ordered pool; keep freed blocks for the next build
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, deviceOrdinal) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (const char* e = std::getenv("KFRT_REFILL_IDLE")) ctx->refillIdle = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
@@ -524,7 +554,7 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->geomTable.release(); ctx->blasInfo.release(); ctx->mats.release(); ctx->texTable.release();
   ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release(); ctx->alProjView.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
-  ctx->instRec.release(); ctx->tlasNodes.release();
+  ctx->instRec.release(); ctx->instBoxInt.release(); ctx->tlasNodes.release();
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
   ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
   ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
@@ -707,12 +737,21 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
 int kfrtBuildBlas(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
   KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  // size the build scratch once, for the largest geometry of this batch
+  uint32_t maxTris = 0;
+  for (auto& g : ctx->geoms)
+    if (g.present && g.dirty && !g.hide) maxTris = std::max(maxTris, g.nIdx / 3);
+  if (maxTris > KF_LEAF_MAX) {
+    int rc = reserveBuild(ctx, ctx->blasBuild, maxTris, false);
+    if (rc) return rc;
+  }
   for (auto& g : ctx->geoms) {
     if (!g.present || !g.dirty) continue;
     int rc = buildOneBlas(ctx, g);
     if (rc) return rc;
     g.dirty = false;
   }
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->blasBuilt = true;
   ctx->tablesDirty = true;
   ctx->tlasBuilt = false;
@@ -744,8 +783,14 @@ static int instanceBoxes(KfrtContext* ctx, bool withSceneBox) {
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->instDev.p, ctx->instHost.data(), sizeof(KfrtInstance) * n,
                                cudaMemcpyHostToDevice, ctx->stream));
   if (withSceneBox) k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
-  k_instance_box<<<n, 128, 0, ctx->stream>>>(ctx->instDev.p, n, ctx->blasInfo.p, uint32_t(ctx->geoms.size()),
-                                             st.primBox.p, withSceneBox ? st.sceneBox.p : nullptr);
+  uint32_t maxVerts = 1;
+  for (const auto& in : ctx->instHost) maxVerts = std::max(maxVerts, ctx->geoms[in.geometryIndex].nVerts);
+  KF_CUDA(ctx, ctx->instBoxInt.ensure(size_t(6) * n));
+  k_instance_box_init<<<gridFor(6 * size_t(n), 256), 256, 0, ctx->stream>>>(ctx->instBoxInt.p, n);
+  k_instance_box<<<dim3(n, gridFor(maxVerts, KF_BOX_CHUNK)), 128, 0, ctx->stream>>>(
+      ctx->instDev.p, n, ctx->blasInfo.p, uint32_t(ctx->geoms.size()), ctx->instBoxInt.p);
+  k_instance_box_finish<<<gridFor(n, 128), 128, 0, ctx->stream>>>(ctx->instBoxInt.p, n, st.primBox.p,
+                                                                   withSceneBox ? st.sceneBox.p : nullptr);
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
