@@ -151,6 +151,7 @@ struct KfrtContext {
   int numSMs = 148;
   size_t batchSlotTarget = size_t(32) << 20;
   int refillIdle = KF_REFILL_IDLE;
+  int instPeriod = KF_INST_PERIOD;
   bool traceLog = false;  // KFRT_TRACE_LOG=1: per-launch ray count and time of every traversal stage on stderr
   size_t wfSlots = 0;
   bool wfMulti = false;
@@ -511,6 +512,7 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
     }
   }
   if (const char* e = std::getenv("KFRT_REFILL_IDLE")) ctx->refillIdle = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("KFRT_INST_PERIOD")) ctx->instPeriod = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
@@ -1021,6 +1023,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.rayCounter = 1;
       te.detailBase = 4;
       te.refillIdle = ctx->refillIdle;
+      te.instPeriod = ctx->instPeriod;
       stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
       logBegin();
       if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);

@@ -31,6 +31,7 @@ namespace kf {
 #ifndef KF_STACK_SHARED
 #define KF_STACK_SHARED 8  // stack entries per lane kept in shared memory (8 KB per block)
 #endif
+#define KF_INST_PERIOD 2  // measured on config 3: 1 -> 2 takes 2.8 % off the closest-hit stage, 4 loses it again
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
 
 struct TraceArgs {
@@ -50,6 +51,7 @@ struct TraceArgs {
   int rayCounter;            // counters[] index that receives the number of rays of this stage
   int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
   int refillIdle;            // refill a warp once this many of its lanes are without a ray
+  int instPeriod;            // the instance phase runs every instPeriod-th iteration (see there)
 };
 
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
 
   bool finished = false;
+  int iter = 0;
   // The first KF_STACK_SHARED entries of the stack live in shared memory, deeper ones (rare) in local
   // memory, and the top entry is mirrored in registers: a pop hands out the register copy at once
   // and reads the entry below it.  (ncu, all-local version: the reload of the entry below was the
@@ -177,7 +180,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     finished = false;
 
     // ---- instance phase (top level): the nearest pending child is an InstNode ------------------
-    if (active && !inBlas && (ng.y & 0xff000000u)) {
+    // Few lanes want it in any one iteration, yet the whole warp pays its ~130 instructions; taking
+    // it only every instPeriod-th iteration lets the requests pile up (a waiting lane idles).
+    if (++iter >= a.instPeriod) iter = 0;
+    if (iter == 0 && active && !inBlas && (ng.y & 0xff000000u)) {
       const uint32_t hits = ng.y;
       const int p = 31 - __clz(hits);
       const uint32_t cslot = uint32_t(p - 24) ^ r.octinv;

@@ -10,7 +10,10 @@ WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
         'smsp__inst_executed_op_global_ld.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum',
-        'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_lsu.sum']
+        'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_lsu.sum',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed']
 def main(path, out=None):
     txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
