@@ -24,6 +24,10 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-pthread",
              "-fvisibility=hidden"]
+# The image's $CXX wrapper (/opt/gcc/bin/g++) resolves -lstdc++ to a static archive: a second copy of
+# the C++ runtime inside the library, exported, which interposes on the process's libstdc++.so (seen
+# as a crash in iostream code under Python).  Link the shared runtime by name instead.
+CXX_LIBS = ["-nostdlib++", "-l:libstdc++.so.6"]
 
 
 def lib_path(name):
@@ -72,7 +76,7 @@ def build_host(force=False):
     if force or _newer(out, deps):
         cxx = os.environ.get("CXX", "g++")
         _run([cxx] + CXX_FLAGS + ["-I", os.path.join(host, "include"), "-I", os.path.join(ROOT, "include"),
-                                  "-o", out] + srcs + ["-L", LIB, "-lkfrt", "-Wl,-rpath,$ORIGIN", "-lz"])
+                                  "-o", out] + srcs + ["-L", LIB, "-lkfrt", "-Wl,-rpath,$ORIGIN", "-lz"] + CXX_LIBS)
     return out
 
 

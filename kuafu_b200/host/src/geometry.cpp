@@ -4,7 +4,9 @@
 // 16 rings) because they are the fixtures of BASELINE configs 1, 3, 4 and 5.
 #include "core/geometry.hpp"
 
+#include <cctype>
 #include <cmath>
+#include <cstring>
 #include <fstream>
 #include <map>
 
@@ -258,17 +260,32 @@ uint32_t globalMaterialIndex(const NiceMaterial& m) {
     if (m == global::materials[j]) return uint32_t(j);
   return registerMaterial(m);
 }
+bool hasExtension(const std::string& path, const char* ext) {
+  const size_t n = std::strlen(ext);
+  if (path.size() < n) return false;
+  for (size_t i = 0; i < n; i++)
+    if (std::tolower(static_cast<unsigned char>(path[path.size() - n + i])) != ext[i]) return false;
+  return true;
+}
 }  // namespace
 
+// import_dae_stl.cpp
+uint32_t importMaterialIndex(const NiceMaterial& m) { return globalMaterialIndex(m); }
+std::vector<std::shared_ptr<Geometry>> loadColladaScene(const std::string& path, bool dynamic);
+std::vector<std::shared_ptr<Geometry>> loadStlScene(const std::string& path, bool dynamic);
+
+// The reference hands every format to Assimp; this build reads Wavefront .obj (below), COLLADA .dae
+// and .stl (import_dae_stl.cpp) and says so for anything else (glTF / FBX / PLY ...).
 std::vector<std::shared_ptr<Geometry>> loadScene(std::string_view fname, bool dynamic) {
   std::string path(fname);
   if (!path.empty() && path[0] != '/' && !global::assetsPath.empty()) {
     std::ifstream probe(path);
     if (!probe.good()) path = global::assetsPath + path;
   }
-  const bool isObj = path.size() > 4 && path.compare(path.size() - 4, 4, ".obj") == 0;
-  if (!isObj)
-    throw std::runtime_error("Failed to load scene: only Wavefront .obj is supported by this build, " + path);
+  if (hasExtension(path, ".dae")) return loadColladaScene(path, dynamic);
+  if (hasExtension(path, ".stl")) return loadStlScene(path, dynamic);
+  if (!hasExtension(path, ".obj"))
+    throw std::runtime_error("Failed to load scene: this build imports .obj, .dae and .stl only, " + path);
   std::ifstream in(path);
   if (!in.good()) throw std::runtime_error("Failed to load scene: cannot open " + path);
 

@@ -1,6 +1,9 @@
 #include "scenes.hpp"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
 #include <random>
 
 namespace kuafu::scenes {
@@ -31,6 +34,23 @@ NiceMaterial material(glm::vec3 diffuse, float specular, float metallic, float r
   m.alpha = 1.0F;
   m.transmission = transmission;
   return m;
+}
+
+// Wavefront text of a Geometry: one v / vt / vn per vertex, faces as i/i/i; %.9g round-trips a float.
+// vt carries 1 - v because loadScene() flips it back (aiProcess_FlipUVs).
+void writeObj(const Geometry& g, const std::string& path) {
+  std::FILE* f = std::fopen(path.c_str(), "w");
+  if (!f) throw std::runtime_error("cannot write " + path);
+  for (const Vertex& v : g.vertices) {
+    std::fprintf(f, "v %.9g %.9g %.9g\n", v.pos.x, v.pos.y, v.pos.z);
+    std::fprintf(f, "vt %.9g %.9g\n", v.texCoord.x, 1.0f - v.texCoord.y);
+    std::fprintf(f, "vn %.9g %.9g %.9g\n", v.normal.x, v.normal.y, v.normal.z);
+  }
+  for (size_t i = 0; i + 2 < g.indices.size(); i += 3) {
+    const unsigned a = g.indices[i] + 1, b = g.indices[i + 1] + 1, c = g.indices[i + 2] + 1;
+    std::fprintf(f, "f %u/%u/%u %u/%u/%u %u/%u/%u\n", a, a, a, b, b, b, c, c, c);
+  }
+  std::fclose(f);
 }
 
 void applyConfig(Kuafu& r, const Recipe& rc, int spp, int depth, bool rr) {
@@ -256,7 +276,23 @@ void skyCube(Scene* scene) {
   scene->setEnvironmentMapFaces(ptr, n);
 }
 
-std::vector<Camera*> loadMillion(Kuafu& r, const Recipe& rc) {  // config 3
+// "via the Assimp path" (BASELINE config 3): the meshes are written out as Wavefront files and come
+// back through loadScene() -- the importer the reference reaches through Assimp -- before the
+// PrincipledBSDF materials are assigned with Geometry::setMaterial().  Positions, normals and face
+// order survive the text round trip bit for bit (9 significant digits); v passes through FlipUVs twice
+// (1 - (1 - v)), which may move it by one ulp.
+std::shared_ptr<Geometry> throughObjFile(const std::shared_ptr<Geometry>& g, const std::string& tag) {
+  const char* tmp = std::getenv("TMPDIR");
+  const std::string path = std::string(tmp && *tmp ? tmp : "/tmp") + "/kuafu_b200_" + tag + ".obj";
+  writeObj(*g, path);
+  const uint32_t matIndex = g->matIndex.empty() ? 0u : g->matIndex.front();
+  auto loaded = loadObj(path, g->dynamic);
+  std::remove(path.c_str());
+  loaded->setMaterial(global::materials[matIndex]);
+  return loaded;
+}
+
+std::vector<Camera*> loadMillion(Kuafu& r, const Recipe& rc, bool viaObj = false) {  // config 3
   applyConfig(r, rc, 64, 8, true);
   Scene* scene = r.getScene();
   Camera* cam = mainCamera(r, rc, 1920, 1080);
@@ -275,6 +311,7 @@ std::vector<Camera*> loadMillion(Kuafu& r, const Recipe& rc) {  // config 3
   NiceMaterial floorMat = material(glm::vec3(0.7f), 0.5f, 0.0f, 0.4f);
   floorMat.diffuseTexPath = noiseTexture(texRng, "million-floor", true);
   auto floor = createYZPlane(true, floorMat);
+  if (viaObj) floor = throughObjFile(floor, "million_floor");
   geoms.push_back(floor);
   const int nMaterials = 16;
   for (int m = 0; m < nMaterials; m++) {
@@ -282,7 +319,8 @@ std::vector<Camera*> loadMillion(Kuafu& r, const Recipe& rc) {  // config 3
     mat.diffuseTexPath = noiseTexture(texRng, "million-d" + std::to_string(m), true);
     mat.roughnessTexPath = noiseTexture(texRng, "million-r" + std::to_string(m), false);
     if (m % 4 == 3) mat.transmissionTexPath = noiseTexture(texRng, "million-t" + std::to_string(m), false);
-    geoms.push_back(createSphere(true, mat));
+    auto sphere = createSphere(true, mat);
+    geoms.push_back(viaObj ? throughObjFile(sphere, "million_sphere" + std::to_string(m)) : sphere);
   }
   scene->setGeometries(geoms);
 
@@ -440,7 +478,43 @@ std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices, uint32_t
   return g;
 }
 
+// "file:<path>": every mesh of an asset file (loadScene: .obj / .dae / .stl), one instance each, a
+// camera that frames the bounding box, a directional light and a light backdrop.
+std::vector<Camera*> loadFile(Kuafu& r, const Recipe& rc, const std::string& path) {
+  applyConfig(r, rc, 16, 8, false);
+  Scene* scene = r.getScene();
+  auto geoms = loadScene(path, false);
+  glm::vec3 lo(3.0e38f), hi(-3.0e38f);
+  for (auto& g : geoms)
+    for (auto& v : g->vertices)
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], v.pos[k]);
+        hi[k] = std::max(hi[k], v.pos[k]);
+      }
+  const glm::vec3 centre = (lo + hi) * 0.5f;
+  const float radius = std::max(0.5f * glm::length(hi - lo), 1e-3f);
+  Camera* cam = mainCamera(r, rc, 640, 480);
+  const glm::vec3 eye = centre + glm::vec3(-1.6f, -1.3f, 0.9f) * radius;
+  cam->setPosition(eye);
+  cam->setFront(glm::normalize(centre - eye));
+  scene->setClearColor({0.7F, 0.75F, 0.8F, 1.0F});
+  auto sun = std::make_shared<DirectionalLight>();
+  sun->direction = {1.0f, 0.8f, -1.2f};
+  sun->color = {1.0f, 1.0f, 1.0f};
+  sun->strength = 4;
+  sun->softness = 0.1f;
+  scene->setDirectionalLight(sun);
+  scene->setGeometries(geoms);
+  std::vector<std::shared_ptr<GeometryInstance>> insts;
+  for (auto& g : geoms) insts.push_back(instance(g, glm::mat4(1.0F)));
+  scene->setGeometryInstances(insts);
+  scene->removeEnvironmentMap();
+  return {cam};
+}
+
 std::vector<Camera*> load(Kuafu& renderer, const Recipe& rc) {
+  if (rc.name.rfind("file:", 0) == 0) return loadFile(renderer, rc, rc.name.substr(5));
+  if (rc.name == "million_obj") return loadMillion(renderer, rc, true);
   if (rc.name == "spheres") return loadSpheres(renderer, rc);
   if (rc.name == "cornell") return loadCornell(renderer, rc);
   if (rc.name == "million") return loadMillion(renderer, rc);
