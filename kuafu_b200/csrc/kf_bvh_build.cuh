@@ -513,7 +513,9 @@ KF_D void quantiseNode(Node8& nd, const Box6& nbIn, const Box6* slotBox, uint32_
 }
 
 #define KF_MEMBER_EMPTY 0x7fffffff
+#ifndef KF_LEAF_MAX
 #define KF_LEAF_MAX 2
+#endif
 static_assert(KF_LEAF_MAX <= 2, "Node8::triMask holds two bits per leaf slot");
 
 struct CollapseArgs {
