@@ -148,6 +148,24 @@ def trace_closest_bytes(cnt, stats):
     return b + ext * (32 + 16), {"nodes": n / max(ext, 1), "triangles": t / max(ext, 1), "instances": i / max(ext, 1)}
 
 
+def alu_line(per_ray, bytes_per_launch, launch_ms, stats):
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mhz = float(json.load(f).get("sm_max_mhz", 1965.0))
+    except (OSError, ValueError):
+        mhz = 1965.0
+    peak = sms * 128 * 2 * mhz * 1e6 / 1e12
+    bytes_per_ray = (int(stats["nodeBytes"]) * per_ray["nodes"] + int(stats["triangleBytes"]) * per_ray["triangles"] +
+                     int(stats["instanceBytes"]) * per_ray["instances"] + 48)
+    rays_per_launch = bytes_per_launch / max(bytes_per_ray, 1.0)
+    flops = rays_per_launch * (136.0 * per_ray["nodes"] + 45.0 * per_ray["triangles"])
+    achieved = flops / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+    return {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x {mhz:.0f} MHz"}
+
+
 def algorithmic_bytes(cnt, stats, n_pixels):
     """SURVEY.md §8.5 accounting: bytes a frame must move given what it visited (layout constants from
     kfrtGetBvhStats: 80 B wide node, 48 B triangle, 80 B instance record)."""
@@ -366,6 +384,11 @@ def main():
                 "algorithmic_bytes_per_launch": kbytes_per_launch, "launches_per_step": k_launches,
                 "launch_ms": k_ms, "per_ray": kper,
                 "share_of_step": stage_ms.get(kname, 0.0) / total_stage,
+                # SURVEY.md §8.5 secondary line: algorithmic FP32 work of the traversal (136 flops per
+                # node step: 8 boxes x 6 slabs x 2 + min/max/compare; 45 per triangle test) against
+                # SMs x 128 lanes x 2 x clock.  Most of a node step is byte unpacking and mask logic,
+                # not flops, so this line sits far below the issue-slot utilisation ncu reports.
+                "alu": alu_line(kper, kbytes_per_launch, k_ms, stats),
                 "stages_ms_per_step": {n: v / args.steps for n, v in stage_ms.items() if v > 0},
                 "frame": {"achieved": frame_achieved, "frac": frame_achieved / peak,
                           "algorithmic_bytes_per_step": abytes, "bytes_per_ray": abytes / max(rays, 1),

@@ -67,6 +67,13 @@ KF_D V3 ccross(V3 a, V3 b) {
 }
 KF_D float cdot(V3 a, V3 b) { return cdot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 KF_D V3 csub3(V3 a, V3 b) { return {csub(a.x, b.x), csub(a.y, b.y), csub(a.z, b.z)}; }
+// Fused arithmetic of the traversal black box (world -> object transform, triangle test): explicit
+// single-rounding FMAs, the same expressions as fdot() / fcross() in oracle/kf_oracle.cpp.
+KF_D float cfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+KF_D float fdot(V3 a, V3 b) { return cfma(a.z, b.z, cfma(a.y, b.y, cmul(a.x, b.x))); }
+KF_D V3 fcross(V3 a, V3 b) {
+  return {cfma(a.y, b.z, -cmul(a.z, b.y)), cfma(a.z, b.x, -cmul(a.x, b.z)), cfma(a.x, b.y, -cmul(a.y, b.x))};
+}
 // column-major 4x4 times (x,y,z,w), summed left to right (oracle mulMat4)
 KF_D void cmulMat4(const float* m, float x, float y, float z, float w, float out[4]) {
 #pragma unroll

@@ -211,15 +211,15 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
           if (DETAIL) tc.entries++;
           if (ng.y & 0xff000000u) push(ng);
           spBlas = sp;
-          // world -> object (contract arithmetic, oracle traceInstance())
+          // world -> object (fused arithmetic, the same expressions as oracle traceInstance())
           const V3 o = mk3(r.ox, r.oy, r.oz), d = mk3(r.dx, r.dy, r.dz);
           V3 oo, od;
-          oo.x = cadd(cdot3(r0.x, r0.y, r0.z, o.x, o.y, o.z), r0.w);
-          oo.y = cadd(cdot3(r1.x, r1.y, r1.z, o.x, o.y, o.z), r1.w);
-          oo.z = cadd(cdot3(r2.x, r2.y, r2.z, o.x, o.y, o.z), r2.w);
-          od.x = cdot3(r0.x, r0.y, r0.z, d.x, d.y, d.z);
-          od.y = cdot3(r1.x, r1.y, r1.z, d.x, d.y, d.z);
-          od.z = cdot3(r2.x, r2.y, r2.z, d.x, d.y, d.z);
+          oo.x = cfma(r0.z, o.z, cfma(r0.y, o.y, cfma(r0.x, o.x, r0.w)));
+          oo.y = cfma(r1.z, o.z, cfma(r1.y, o.y, cfma(r1.x, o.x, r1.w)));
+          oo.z = cfma(r2.z, o.z, cfma(r2.y, o.y, cfma(r2.x, o.x, r2.w)));
+          od.x = cfma(r0.z, d.z, cfma(r0.y, d.y, cmul(r0.x, d.x)));
+          od.y = cfma(r1.z, d.z, cfma(r1.y, d.y, cmul(r1.x, d.x)));
+          od.z = cfma(r2.z, d.z, cfma(r2.y, d.y, cmul(r2.x, d.x)));
           r = setupRay(oo, od);
           nodes = reinterpret_cast<const Node8*>(ptrs.x);
           nonOpaque = (ptrs.y & 1ull) != 0;
@@ -257,17 +257,17 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
       const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + __popc((tg.y >> 16) & ((1u << b) - 1u)));
       const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
       if (DETAIL) tc.tris++;
-      // Moller-Trumbore, contract arithmetic, same operation order as oracle intersectTri()
+      // Moller-Trumbore, fused arithmetic, same expressions as oracle intersectTri()
       const V3 dd = mk3(r.dx, r.dy, r.dz);
       const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
-      const V3 pv = ccross(dd, E2);
-      const float det = cdot(E1, pv);
+      const V3 pv = fcross(dd, E2);
+      const float det = fdot(E1, pv);
       const float inv = cdiv(1.0f, det);
       const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(v0.x, v0.y, v0.z));
-      const float u = cmul(cdot(tv, pv), inv);
-      const V3 qv = ccross(tv, E1);
-      const float v = cmul(cdot(dd, qv), inv);
-      const float t = cmul(cdot(E2, qv), inv);
+      const float u = cmul(fdot(tv, pv), inv);
+      const V3 qv = fcross(tv, E1);
+      const float v = cmul(fdot(dd, qv), inv);
+      const float t = cmul(fdot(E2, qv), inv);
       const int32_t prim = int32_t(__float_as_uint(v0.w));
       bool ok = det != 0.0f && (u >= 0.0f && u <= 1.0f) && (v >= 0.0f && cadd(u, v) <= 1.0f) && t > tmin;
       ok = ok && (t < hit.t || (t == hit.t && hit.inst >= 0 &&

@@ -30,9 +30,10 @@
 //       PathTrace.rahit; the two agree statistically, tests/test_cpu_ref_pin.py).
 //
 // Arithmetic contract (shared with the CUDA kernels so that hit buffers can be bit-exact):
-// IEEE-754 binary32, round-to-nearest, NO fused multiply-add (compile with -ffp-contract=off),
-// dot(a,b) = (a.x*b.x + a.y*b.y) + a.z*b.z, normalize(v) = v * (1 / sqrt(dot(v,v))),
-// mat*vec sums left to right.  Transcendentals (sin, cos, pow, exp2, tan) are libm and are the
+// IEEE-754 binary32, round-to-nearest, NO fused multiply-add in anything transcribed from the shaders
+// (compile with -ffp-contract=off), dot(a,b) = (a.x*b.x + a.y*b.y) + a.z*b.z,
+// normalize(v) = v * (1 / sqrt(dot(v,v))), mat*vec sums left to right.  The traversal black box
+// (world -> object transform, triangle test) uses explicit fused multiply-adds, see fdot().  Transcendentals (sin, cos, pow, exp2, tan) are libm and are the
 // reason radiance parity is toleranced rather than bit-exact.
 //
 // Every function cites the reference file:line it follows (paths relative to the reference root).
@@ -487,21 +488,31 @@ struct Hit {
   bool front;
 };
 
+// Fused arithmetic of the traversal black box.  What traceRayEXT does inside the driver -- the
+// world -> object ray transform and the ray / triangle test -- is not shader code, so its arithmetic is
+// ours to define; it is defined with fused multiply-adds (one rounding per fma, std::fma here,
+// __fmaf_rn on the device), which is what a GPU executes natively.  Everything transcribed from the
+// GLSL keeps the unfused contract of the file header.
+static inline float fdot(V3 a, V3 b) { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+static inline V3 fcross(V3 a, V3 b) {
+  return {std::fma(a.y, b.z, -(a.z * b.y)), std::fma(a.z, b.x, -(a.x * b.z)), std::fma(a.x, b.y, -(a.y * b.x))};
+}
+
 // Moller-Trumbore in object space, no culling (instances use TriangleFacingCullDisable,
 // src/core/rt/rt.cpp:134).  The operation order below is the bit-exactness contract.
 static inline bool intersectTri(const Tri& tr, V3 o, V3 d, float& t, float& u, float& v,
                                 float& det) {
-  V3 p = cross(d, tr.e2);
-  det = dot(tr.e1, p);
+  V3 p = fcross(d, tr.e2);
+  det = fdot(tr.e1, p);
   if (det == 0.0f) return false;
   float inv = 1.0f / det;
   V3 tv = o - tr.v0;
-  u = dot(tv, p) * inv;
+  u = fdot(tv, p) * inv;
   if (!(u >= 0.0f && u <= 1.0f)) return false;
-  V3 q = cross(tv, tr.e1);
-  v = dot(d, q) * inv;
+  V3 q = fcross(tv, tr.e1);
+  v = fdot(d, q) * inv;
   if (!(v >= 0.0f && u + v <= 1.0f)) return false;
-  t = dot(tr.e2, q) * inv;
+  t = fdot(tr.e2, q) * inv;
   return true;
 }
 
@@ -566,12 +577,13 @@ struct Tracer {
     const Geometry& g = s.geoms[r.geom];
     if (!g.present || g.hide || g.tris.empty()) return;
     V3 oo, od;
-    oo.x = ((r.inv[0][0] * o.x + r.inv[0][1] * o.y) + r.inv[0][2] * o.z) + r.inv[0][3];
-    oo.y = ((r.inv[1][0] * o.x + r.inv[1][1] * o.y) + r.inv[1][2] * o.z) + r.inv[1][3];
-    oo.z = ((r.inv[2][0] * o.x + r.inv[2][1] * o.y) + r.inv[2][2] * o.z) + r.inv[2][3];
-    od.x = (r.inv[0][0] * d.x + r.inv[0][1] * d.y) + r.inv[0][2] * d.z;
-    od.y = (r.inv[1][0] * d.x + r.inv[1][1] * d.y) + r.inv[1][2] * d.z;
-    od.z = (r.inv[2][0] * d.x + r.inv[2][1] * d.y) + r.inv[2][2] * d.z;
+    // world -> object, fused (see fdot): row . o + translation, row . d
+    oo.x = std::fma(r.inv[0][2], o.z, std::fma(r.inv[0][1], o.y, std::fma(r.inv[0][0], o.x, r.inv[0][3])));
+    oo.y = std::fma(r.inv[1][2], o.z, std::fma(r.inv[1][1], o.y, std::fma(r.inv[1][0], o.x, r.inv[1][3])));
+    oo.z = std::fma(r.inv[2][2], o.z, std::fma(r.inv[2][1], o.y, std::fma(r.inv[2][0], o.x, r.inv[2][3])));
+    od.x = std::fma(r.inv[0][2], d.z, std::fma(r.inv[0][1], d.y, r.inv[0][0] * d.x));
+    od.y = std::fma(r.inv[1][2], d.z, std::fma(r.inv[1][1], d.y, r.inv[1][0] * d.x));
+    od.z = std::fma(r.inv[2][2], d.z, std::fma(r.inv[2][1], d.y, r.inv[2][0] * d.x));
     if (brute) {
       for (uint32_t p = 0; p < g.tris.size(); p++) {
         testTri(g, i, p, oo, od, tmin, anyHit, seed, best, found);
