@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
       const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
       const V3 pv = fcross(dd, E2);
       const float det = fdot(E1, pv);
-      const float inv = cdiv(1.0f, det);
+      const float inv = __frcp_rn(det);  // correctly rounded 1 / det, the oracle's `1.0f / det`
       const V3 tv = csub3(mk3(r.ox, r.oy, r.oz), mk3(v0.x, v0.y, v0.z));
       const float u = cmul(fdot(tv, pv), inv);
       const V3 qv = fcross(tv, E1);
