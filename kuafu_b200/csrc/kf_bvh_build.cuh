@@ -126,6 +126,7 @@ struct BlasInfo {
   const KfrtVertex* verts;
   const uint32_t* idx;
   const uint32_t* matIndex;
+  const ShadeTri* shade;
   float box[6];
   uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque
   uint32_t nVerts;
@@ -169,7 +170,7 @@ __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_
   rec.verts = g < nBlas ? blas[g].verts : nullptr;
   rec.idx = g < nBlas ? blas[g].idx : nullptr;
   rec.matIndex = g < nBlas ? blas[g].matIndex : nullptr;
-  rec.pad = 0;
+  rec.shade = g < nBlas ? blas[g].shade : nullptr;
   recs[i] = rec;
   // the record the traversal reads, in the top-level node array
   InstNode in;
@@ -746,6 +747,31 @@ __global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers
   Node8 nd = nodes[w];
   quantiseNode(nd, nb, slotBox, used);
   nodes[w] = nd;
+}
+
+// Shading records in primitive order (see ShadeTri): plain copies of the vertex attributes.
+__global__ void k_write_shade_tris(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                   const uint32_t* __restrict__ matIndex, uint32_t n, ShadeTri* __restrict__ out) {
+  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prim >= n) return;
+  const KfrtVertex& a = verts[idx[3 * prim + 0]];
+  const KfrtVertex& b = verts[idx[3 * prim + 1]];
+  const KfrtVertex& c = verts[idx[3 * prim + 2]];
+  ShadeTri t;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    t.n0[k] = a.normal[k];
+    t.n1[k] = b.normal[k];
+    t.n2[k] = c.normal[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    t.uv0[k] = a.texCoord[k];
+    t.uv1[k] = b.texCoord[k];
+    t.uv2[k] = c.texCoord[k];
+  }
+  t.matIndex = matIndex[prim];
+  out[prim] = t;
 }
 
 // Triangles in leaf order: v0, e1 = v1 - v0, e2 = v2 - v0 (single IEEE subtractions, like the oracle).

@@ -140,12 +140,24 @@ static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 // Per-instance shading record, indexed by instance: world->object (for the normal transform) and the
 // geometry's attribute tables, so that the attribute gather of a hit is instance -> indices ->
 // vertices with no detour over the instance SSBO and the geometry table.  80 bytes = 5 x 16 B loads.
+// What shading a hit needs of its triangle, gathered once per BLAS build in primitive order (64 bytes
+// = 4 x 16 B loads): the three vertex normals, the three texture coordinates and the material index.
+// It replaces the reference's chain indices -> three 48-byte vertices -> matIndices[prim]
+// (PathTrace.rchit:66-98: 12 + 144 + 4 scattered bytes behind one more dependent load) with the same
+// bits read from one place.
+struct __align__(16) ShadeTri {
+  float n0[3], n1[3], n2[3];
+  float uv0[2], uv1[2], uv2[2];
+  uint32_t matIndex;
+};
+static_assert(sizeof(ShadeTri) == 64, "ShadeTri must be 64 bytes");
+
 struct __align__(16) InstRec {
   float inv[12];            // world->object, 3 rows x 4 columns
   const KfrtVertex* verts;  // geometry tables (reference PathTrace.rchit:66-98)
   const uint32_t* idx;
   const uint32_t* matIndex;
-  uint64_t pad;
+  const ShadeTri* shade;    // per-primitive shading records of the geometry
 };
 static_assert(sizeof(InstRec) == 80, "InstRec must be 80 bytes");
 

@@ -62,11 +62,12 @@ struct GeomHost {
   uint32_t* matIndex = nullptr;
   Node8* nodes = nullptr;
   Tri48* tris = nullptr;
+  ShadeTri* shade = nullptr;
   uint32_t nNodes = 0;
   float box[6] = {0, 0, 0, 0, 0, 0};
   void freeAll() {
-    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodes); cudaFree(tris);
-    verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; tris = nullptr;
+    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodes); cudaFree(tris); cudaFree(shade);
+    verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; tris = nullptr; shade = nullptr;
     present = false;
     nNodes = 0;
   }
@@ -334,8 +335,10 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   // nodes / triangles come from the stream-ordered pool: no device-wide synchronisation per BLAS
   if (g.nodes) cudaFreeAsync(g.nodes, ctx->stream);
   if (g.tris) cudaFreeAsync(g.tris, ctx->stream);
+  if (g.shade) cudaFreeAsync(g.shade, ctx->stream);
   g.nodes = nullptr;
   g.tris = nullptr;
+  g.shade = nullptr;
   g.nNodes = 0;
   const uint32_t nTris = g.nIdx / 3;
   if (nTris == 0 || g.hide) return KFRT_OK;
@@ -355,6 +358,8 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   KF_CUDA(ctx, cudaMemcpyAsync(g.nodes, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice,
                                ctx->stream));
   k_write_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, st.outPrim.p, nTris, g.tris);
+  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.shade), sizeof(ShadeTri) * nTris, ctx->stream));
+  k_write_shade_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, g.matIndex, nTris, g.shade);
   orderedBoxToFloat(ib, g.box);
   g.nNodes = st.nWide;
   return KFRT_OK;
@@ -376,6 +381,7 @@ static int uploadTables(KfrtContext* ctx) {
     infos[i].verts = g.verts;
     infos[i].idx = g.idx;
     infos[i].matIndex = g.matIndex;
+    infos[i].shade = g.shade;
     infos[i].nVerts = g.nVerts;
     std::memcpy(infos[i].box, g.box, sizeof(g.box));
     infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u);

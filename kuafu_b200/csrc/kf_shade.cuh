@@ -190,21 +190,13 @@ KF_D bool shadeSurface(const SceneDev& sc, const Hit& h, V3 rayO, V3 rayD, uint3
                        V3& L, V3& weight, V3& albedo, V3& emission, uint32_t& texFetches) {
   const float4* ip = reinterpret_cast<const float4*>(sc.inst + h.inst);
   const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
-  const ulonglong2 p01 = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
   const ulonglong2 p23 = __ldg(reinterpret_cast<const ulonglong2*>(ip + 4));
-  struct { const KfrtVertex* verts; const uint32_t* idx; const uint32_t* matIndex; } g;
-  g.verts = reinterpret_cast<const KfrtVertex*>(p01.x);
-  g.idx = reinterpret_cast<const uint32_t*>(p01.y);
-  g.matIndex = reinterpret_cast<const uint32_t*>(p23.x);
-  const uint32_t i0 = __ldg(g.idx + 3 * h.prim + 0), i1 = __ldg(g.idx + 3 * h.prim + 1),
-                 i2 = __ldg(g.idx + 3 * h.prim + 2);
-  // vertex = 3 x float4: (pos.xyz, n.x) (n.y, n.z, c.r, c.g) (c.b, u, v, pad)   [rchit:52-64]
-  const float4* vb = reinterpret_cast<const float4*>(g.verts);
-  const float4 a0 = __ldg(vb + 3 * size_t(i0)), a1 = __ldg(vb + 3 * size_t(i0) + 1), a2v = __ldg(vb + 3 * size_t(i0) + 2);
-  const float4 b0 = __ldg(vb + 3 * size_t(i1)), b1 = __ldg(vb + 3 * size_t(i1) + 1), b2v = __ldg(vb + 3 * size_t(i1) + 2);
-  const float4 c0 = __ldg(vb + 3 * size_t(i2)), c1 = __ldg(vb + 3 * size_t(i2) + 1), c2v = __ldg(vb + 3 * size_t(i2) + 2);
+  // normals, texture coordinates and material index of the triangle: one 64-byte ShadeTri record
+  // (the same bits the reference reads through indices -> vertices -> matIndices, rchit:52-98)
+  const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const ShadeTri*>(p23.y) + h.prim);
+  const float4 s0 = __ldg(sp + 0), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2), s3 = __ldg(sp + 3);
   const float bx = 1.0f - h.u - h.v, by = h.u, bz = h.v;
-  const V3 n0 = mk3(a0.w, a1.x, a1.y), n1 = mk3(b0.w, b1.x, b1.y), n2 = mk3(c0.w, c1.x, c1.y);
+  const V3 n0 = mk3(s0.x, s0.y, s0.z), n1 = mk3(s0.w, s1.x, s1.y), n2 = mk3(s1.z, s1.w, s2.x);
   const V3 ln = n0 * bx + n1 * by + n2 * bz;
   V3 wn;
   wn.x = (ln.x * r0.x + ln.y * r1.x) + ln.z * r2.x;
@@ -212,9 +204,9 @@ KF_D bool shadeSurface(const SceneDev& sc, const Hit& h, V3 rayO, V3 rayD, uint3
   wn.z = (ln.x * r0.z + ln.y * r1.z) + ln.z * r2.z;
   V3 N = normalize(wn);
   const V3 worldPos = rayO + rayD * h.t;
-  const float uvx = (a2v.y * bx + b2v.y * by) + c2v.y * bz;
-  const float uvy = (a2v.z * bx + b2v.z * by) + c2v.z * bz;
-  const uint32_t matIndex = __ldg(g.matIndex + h.prim);
+  const float uvx = (s2.y * bx + s2.w * by) + s3.y * bz;
+  const float uvy = (s2.z * bx + s3.x * by) + s3.z * bz;
+  const uint32_t matIndex = __float_as_uint(s3.w);
   const float4* mp = reinterpret_cast<const float4*>(sc.mats + matIndex);
   const float4 m0 = __ldg(mp + 0), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
   const int4 m4 = __ldg(reinterpret_cast<const int4*>(mp + 4));
