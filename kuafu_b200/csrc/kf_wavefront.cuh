@@ -176,15 +176,60 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
     a.b.counts[4] = 0;  // fetch cursors of the next closest-hit / occlusion stages
     a.b.counts[5] = 0;
   }
+  // The block re-deals its 128 queue entries before shading them: hits first, misses last.  A miss
+  // is a short path (environment lookup), a hit a long one (gather, textures, BSDF, light sample); in
+  // bounce order the two are mixed within every warp, so every warp walked the long path.  After the
+  // deal whole warps are miss-only and skip it.
+  __shared__ uint32_t sSlot[128];
+  __shared__ int sHitB[128];
+  __shared__ uint32_t sClass[2][4];  // per warp: hits, misses
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
-    const uint32_t i = base + threadIdx.x;
-    const bool valid = i < count;
-    bool toNext = false, toShadow = false, isHit = false;
+    bool valid;
     uint32_t slot = 0;
+    int hB = -1;
+    {
+      const uint32_t i = base + threadIdx.x;
+      const bool have = i < count;
+      uint32_t mySlot = 0;
+      int myHit = -1;
+      if (have) {
+        mySlot = queue[i];
+        myHit = a.b.hitB[mySlot];
+      }
+      const uint32_t hitMask = __ballot_sync(0xffffffffu, have && myHit != -1);
+      const uint32_t missMask = __ballot_sync(0xffffffffu, have && myHit == -1);
+      if (lane == 0) {
+        sClass[0][warp] = __popc(hitMask);
+        sClass[1][warp] = __popc(missMask);
+      }
+      __syncthreads();
+      uint32_t hitsBefore = 0, missesBefore = 0, hitsTotal = 0, missesTotal = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < 4; w++) {
+        const uint32_t h = sClass[0][w], m = sClass[1][w];
+        if (w < warp) { hitsBefore += h; missesBefore += m; }
+        hitsTotal += h;
+        missesTotal += m;
+      }
+      if (have) {
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t pos = myHit != -1 ? hitsBefore + __popc(hitMask & below)
+                                         : hitsTotal + missesBefore + __popc(missMask & below);
+        sSlot[pos] = mySlot;
+        sHitB[pos] = myHit;
+      }
+      __syncthreads();
+      valid = threadIdx.x < hitsTotal + missesTotal;
+      if (valid) {
+        slot = sSlot[threadIdx.x];
+        hB = sHitB[threadIdx.x];
+      }
+      __syncthreads();  // the arrays are rewritten by the next round
+    }
+    bool toNext = false, toShadow = false, isHit = false;
     if (valid) {
-      slot = queue[i];
       const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[slot];
-      const int hB = a.b.hitB[slot];
       const float4 sw = a.b.stateW[slot];
       float4 sc4 = a.b.stateC[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
