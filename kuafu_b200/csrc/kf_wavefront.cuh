@@ -180,11 +180,17 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
   // is a short path (environment lookup), a hit a long one (gather, textures, BSDF, light sample); in
   // bounce order the two are mixed within every warp, so every warp walked the long path.  After the
   // deal whole warps are miss-only and skip it.
-  __shared__ uint32_t sSlot[128];
-  __shared__ int sHitB[128];
-  __shared__ uint32_t sClass[2][4];  // per warp: hits, misses
+  // (two copies of the staging arrays, used in turn: a warp still reading round n is separated from
+  // the writers of round n + 2 by the two barriers of round n + 1)
+  __shared__ uint32_t sSlotBuf[2][128];
+  __shared__ int sHitBuf[2][128];
+  __shared__ uint32_t sClassBuf[2][2][4];  // per warp: hits, misses
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
+  uint32_t round = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride, round ^= 1u) {
+    uint32_t* sSlot = sSlotBuf[round];
+    int* sHitB = sHitBuf[round];
+    uint32_t(*sClass)[4] = sClassBuf[round];
     bool valid;
     uint32_t slot = 0;
     int hB = -1;
@@ -225,7 +231,6 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
         slot = sSlot[threadIdx.x];
         hB = sHitB[threadIdx.x];
       }
-      __syncthreads();  // the arrays are rewritten by the next round
     }
     bool toNext = false, toShadow = false, isHit = false;
     if (valid) {
