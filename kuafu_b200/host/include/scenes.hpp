@@ -21,7 +21,7 @@ struct Recipe {
 ///   "active"       config 4  eActive (Example.hpp:479-645) with an IR dot-pattern projector, stereo pair
 ///   "articulated"  config 5  2048 link instances (64 chains x 32 links), 64 cameras, animate() per frame
 ///   "million_obj"  config 3 with every mesh written to a Wavefront file and read back by loadScene()
-///   "file:<path>"  the meshes of an asset file (.obj / .dae / .stl), framed by one camera
+///   "file:<path>"  the meshes of an asset file (.obj / .dae / .stl / .gltf / .glb), framed by one camera
 KUAFU_API std::vector<Camera*> load(Kuafu& renderer, const Recipe& recipe);
 
 /// Per-frame actor motion of "articulated": deterministic joint angles -> GeometryInstance::setTransform.

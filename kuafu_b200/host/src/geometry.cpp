@@ -273,9 +273,11 @@ bool hasExtension(const std::string& path, const char* ext) {
 uint32_t importMaterialIndex(const NiceMaterial& m) { return globalMaterialIndex(m); }
 std::vector<std::shared_ptr<Geometry>> loadColladaScene(const std::string& path, bool dynamic);
 std::vector<std::shared_ptr<Geometry>> loadStlScene(const std::string& path, bool dynamic);
+std::vector<std::shared_ptr<Geometry>> loadGltfScene(const std::string& path, bool dynamic);  // import_gltf.cpp
 
 // The reference hands every format to Assimp; this build reads Wavefront .obj (below), COLLADA .dae
-// and .stl (import_dae_stl.cpp) and says so for anything else (glTF / FBX / PLY ...).
+// and .stl (import_dae_stl.cpp), glTF 2.0 .gltf / .glb (import_gltf.cpp) and says so for anything
+// else (FBX / PLY / 3DS ...).
 std::vector<std::shared_ptr<Geometry>> loadScene(std::string_view fname, bool dynamic) {
   std::string path(fname);
   if (!path.empty() && path[0] != '/' && !global::assetsPath.empty()) {
@@ -284,8 +286,9 @@ std::vector<std::shared_ptr<Geometry>> loadScene(std::string_view fname, bool dy
   }
   if (hasExtension(path, ".dae")) return loadColladaScene(path, dynamic);
   if (hasExtension(path, ".stl")) return loadStlScene(path, dynamic);
+  if (hasExtension(path, ".gltf") || hasExtension(path, ".glb")) return loadGltfScene(path, dynamic);
   if (!hasExtension(path, ".obj"))
-    throw std::runtime_error("Failed to load scene: this build imports .obj, .dae and .stl only, " + path);
+    throw std::runtime_error("Failed to load scene: this build imports .obj, .dae, .stl, .gltf and .glb only, " + path);
   std::ifstream in(path);
   if (!in.good()) throw std::runtime_error("Failed to load scene: cannot open " + path);
 

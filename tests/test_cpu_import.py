@@ -135,10 +135,74 @@ def test_collada_transforms_polylists_and_materials(built, tmp_path):
     assert np.isclose(m["roughness"], 1.0 - np.sqrt(30.0 - 5.0) * 0.025)
 
 
+def _gltf_doc(bin_len, uri=None):
+    """A unit quad (4 vertices, 2 indexed triangles, u16 indices) under a node translated by (1, 2, 3)
+    inside a parent scaled by 2, with a metallic-roughness material and the ior / transmission
+    extensions."""
+    buf = {"byteLength": bin_len}
+    if uri is not None:
+        buf["uri"] = uri
+    return {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+        "nodes": [{"scale": [2, 2, 2], "children": [1]}, {"translation": [1, 2, 3], "mesh": 0}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 2}, "indices": 3, "material": 0}]}],
+        "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.2, 0.4, 0.6, 0.5], "metallicFactor": 0.25, "roughnessFactor": 0.75},
+                       "alphaMode": "BLEND", "emissiveFactor": [0, 0, 0],
+                       "extensions": {"KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 0.5}}}],
+        "buffers": [buf],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 48}, {"buffer": 0, "byteOffset": 48, "byteLength": 48},
+                        {"buffer": 0, "byteOffset": 96, "byteLength": 32}, {"buffer": 0, "byteOffset": 128, "byteLength": 12}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3", "min": [0, 0, 0], "max": [1, 1, 0]},
+                      {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC3"},
+                      {"bufferView": 2, "componentType": 5126, "count": 4, "type": "VEC2"},
+                      {"bufferView": 3, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+    }
+
+
+def _gltf_bin():
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (4, 1))
+    uv = np.array([[0, 0], [1, 0], [1, 0.25], [0, 0.25]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    return pos.tobytes() + nrm.tobytes() + uv.tobytes() + idx.tobytes()
+
+
+@pytest.mark.parametrize("container", ["glb", "gltf+bin", "gltf+base64"])
+def test_gltf_import(built, tmp_path, container):
+    import base64
+    import json
+    blob = _gltf_bin()
+    if container == "glb":
+        js = json.dumps(_gltf_doc(len(blob))).encode()
+        js += b" " * (-len(js) % 4)
+        body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+        path = str(tmp_path / "quad.glb")
+        open(path, "wb").write(b"glTF" + struct.pack("<II", 2, 12 + len(body)) + body)
+    elif container == "gltf+bin":
+        open(str(tmp_path / "quad.bin"), "wb").write(blob)
+        path = str(tmp_path / "quad.gltf")
+        open(path, "w").write(json.dumps(_gltf_doc(len(blob), "quad.bin")))
+    else:
+        path = str(tmp_path / "quad64.gltf")
+        uri = "data:application/octet-stream;base64," + base64.b64encode(blob).decode()
+        open(path, "w").write(json.dumps(_gltf_doc(len(blob), uri)))
+    ws = _load("file:" + path)
+    assert len(ws.geoms) == 1
+    v, idx, mi, opaque, hide = ws.geoms[0]
+    assert np.array_equal(idx, [0, 1, 2, 0, 2, 3]) and v.size == 4       # indexed, as the accessors hold them
+    assert np.array_equal(v["pos"], [[2, 4, 6], [4, 4, 6], [4, 6, 6], [2, 6, 6]])   # 2 * (p + (1, 2, 3))
+    assert np.allclose(v["normal"], [0, 0, 1], atol=1e-6)
+    assert np.array_equal(v["texCoord"], [[0, 1], [1, 1], [1, 0.75], [0, 0.75]])    # FlipUVs
+    m = ws.mats[int(mi[0])]
+    assert np.allclose(m["diffuse"][:3], [0.2, 0.4, 0.6]) and m["alpha"] == np.float32(0.5) and not opaque
+    assert m["metallic"] == np.float32(0.25) and m["roughness"] == np.float32(0.75)
+    assert m["ior"] == np.float32(1.33) and m["transmission"] == np.float32(0.5)
+
+
 def test_unsupported_format_fails_loudly(built, tmp_path):
-    path = str(tmp_path / "x.gltf")
+    path = str(tmp_path / "x.fbx")
     open(path, "w").write("{}")
-    with pytest.raises(RuntimeError, match="imports .obj, .dae and .stl only"):
+    with pytest.raises(RuntimeError, match="imports .obj, .dae, .stl, .gltf and .glb only"):
         _load("file:" + path)
 
 
