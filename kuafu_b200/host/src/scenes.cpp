@@ -494,7 +494,7 @@ std::vector<Camera*> loadFile(Kuafu& r, const Recipe& rc, const std::string& pat
   const glm::vec3 centre = (lo + hi) * 0.5f;
   const float radius = std::max(0.5f * glm::length(hi - lo), 1e-3f);
   Camera* cam = mainCamera(r, rc, 640, 480);
-  const glm::vec3 eye = centre + glm::vec3(-1.6f, -1.3f, 0.9f) * radius;
+  const glm::vec3 eye = centre + glm::vec3(-1.2f, -1.0f, 0.7f) * radius;
   cam->setPosition(eye);
   cam->setFront(glm::normalize(centre - eye));
   scene->setClearColor({0.7F, 0.75F, 0.8F, 1.0F});
