@@ -34,21 +34,29 @@ namespace {
 
 thread_local std::string g_createError = "";
 
+// Grow-only device buffer.  Storage comes from the device's stream-ordered pool (kept by
+// kfrtCreate's release threshold), so that a context created after another one in the same process
+// re-uses its memory instead of going back to cudaMalloc (measured: 8 - 140 ms for the scratch of a
+// 250 k-triangle build, against 4 ms for the build itself).  Growing or releasing a buffer
+// synchronises the device, exactly as the cudaFree it replaces did.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    release();
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T), cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
     if (e == cudaSuccess) cap = n;
+    else p = nullptr;
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaDeviceSynchronize();
+      cudaFreeAsync(p, cudaStreamPerThread);
+    }
     p = nullptr;
     cap = 0;
   }
