@@ -269,6 +269,9 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     int rc = reserveBuild(ctx, st, n, tlas);
     if (rc) return rc;
   }
+  // top level: the InstNode slots of the array are written later (k_instance_setup, into the copy the
+  // traversal reads); give them defined bytes until then
+  if (tlas) KF_CUDA(ctx, cudaMemsetAsync(st.outNodes.p, 0, sizeof(Node8) * maxNodes, ctx->stream));
   if (tlas && n == 1) {
     k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, st.outNodes.p, st.wideBinary.p,
                                                       st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
