@@ -749,6 +749,31 @@ __global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers
   nodes[w] = nd;
 }
 
+// Bounding sphere of a geometry in object space: centre of its box, squared radius over all its
+// vertices (a float that is >= 0 orders like its bits, so atomicMax on the bits does the reduction).
+// It lives in the 80-byte record in front of the BLAS root (nodes[-1]) and is tested when a ray enters
+// the instance (kf_trace.cuh): the world box of a rotated or round object is far from tight, and every
+// needless entry costs a root node step or more.
+__global__ void k_blas_sphere(const KfrtVertex* __restrict__ verts, uint32_t nVerts, const int* __restrict__ sceneBox,
+                              float* __restrict__ header /* cx, cy, cz, r^2 (bits) */) {
+  const float cx = 0.5f * (orderedToFloat(sceneBox[0]) + orderedToFloat(sceneBox[3]));
+  const float cy = 0.5f * (orderedToFloat(sceneBox[1]) + orderedToFloat(sceneBox[4]));
+  const float cz = 0.5f * (orderedToFloat(sceneBox[2]) + orderedToFloat(sceneBox[5]));
+  float r2 = 0.0f;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nVerts; v += gridDim.x * blockDim.x) {
+    const float dx = verts[v].pos[0] - cx, dy = verts[v].pos[1] - cy, dz = verts[v].pos[2] - cz;
+    r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(header) + 3, __float_as_uint(r2));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    header[0] = cx;
+    header[1] = cy;
+    header[2] = cz;
+  }
+}
+
 // Shading records in primitive order (see ShadeTri): plain copies of the vertex attributes.
 __global__ void k_write_shade_tris(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
                                    const uint32_t* __restrict__ matIndex, uint32_t n, ShadeTri* __restrict__ out) {

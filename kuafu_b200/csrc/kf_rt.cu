@@ -68,14 +68,15 @@ struct GeomHost {
   KfrtVertex* verts = nullptr;
   uint32_t* idx = nullptr;
   uint32_t* matIndex = nullptr;
-  Node8* nodes = nullptr;
+  Node8* nodes = nullptr;       // root; the record in front of it (nodesAlloc) holds the bounding sphere
+  Node8* nodesAlloc = nullptr;
   Tri48* tris = nullptr;
   ShadeTri* shade = nullptr;
   uint32_t nNodes = 0;
   float box[6] = {0, 0, 0, 0, 0, 0};
   void freeAll() {
-    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodes); cudaFree(tris); cudaFree(shade);
-    verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; tris = nullptr; shade = nullptr;
+    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodesAlloc); cudaFree(tris); cudaFree(shade);
+    verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; nodesAlloc = nullptr; tris = nullptr; shade = nullptr;
     present = false;
     nNodes = 0;
   }
@@ -344,10 +345,11 @@ static void orderedBoxToFloat(const int* ib, float* out) {
 
 static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   // nodes / triangles come from the stream-ordered pool: no device-wide synchronisation per BLAS
-  if (g.nodes) cudaFreeAsync(g.nodes, ctx->stream);
+  if (g.nodesAlloc) cudaFreeAsync(g.nodesAlloc, ctx->stream);
   if (g.tris) cudaFreeAsync(g.tris, ctx->stream);
   if (g.shade) cudaFreeAsync(g.shade, ctx->stream);
   g.nodes = nullptr;
+  g.nodesAlloc = nullptr;
   g.tris = nullptr;
   g.shade = nullptr;
   g.nNodes = 0;
@@ -364,7 +366,11 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   int rc = buildWideBvh(ctx, st, nTris, false);
   if (rc) return rc;
   if (nTris <= KF_LEAF_MAX) KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.nodes), sizeof(Node8) * st.nWide, ctx->stream));
+  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.nodesAlloc), sizeof(Node8) * (size_t(st.nWide) + 1), ctx->stream));
+  g.nodes = g.nodesAlloc + 1;
+  KF_CUDA(ctx, cudaMemsetAsync(g.nodesAlloc, 0, sizeof(Node8), ctx->stream));
+  k_blas_sphere<<<std::min<unsigned>(gridFor(g.nVerts, 256), unsigned(ctx->numSMs) * 4u), 256, 0, ctx->stream>>>(
+      g.verts, g.nVerts, st.sceneBox.p, reinterpret_cast<float*>(g.nodesAlloc));
   KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(g.nodes, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice,
                                ctx->stream));

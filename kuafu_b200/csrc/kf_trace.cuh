@@ -207,10 +207,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(ip) + 0);
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
           const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);
-          // what is left of this top-level node waits on the stack, below the bottom-level entries
-          if (DETAIL) tc.entries++;
-          if (ng.y & 0xff000000u) push(ng);
-          spBlas = sp;
+          // bounding sphere of the geometry, in the record in front of its root
+          const float4 sph = __ldg(reinterpret_cast<const float4*>(ptrs.x) - 5);
           // world -> object (fused arithmetic, the same expressions as oracle traceInstance())
           const V3 o = mk3(r.ox, r.oy, r.oz), d = mk3(r.dx, r.dy, r.dz);
           V3 oo, od;
@@ -220,13 +218,34 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
           od.x = cfma(r0.z, d.z, cfma(r0.y, d.y, cmul(r0.x, d.x)));
           od.y = cfma(r1.z, d.z, cfma(r1.y, d.y, cmul(r1.x, d.x)));
           od.z = cfma(r2.z, d.z, cfma(r2.y, d.y, cmul(r2.x, d.x)));
-          r = setupRay(oo, od);
-          nodes = reinterpret_cast<const Node8*>(ptrs.x);
-          nonOpaque = (ptrs.y & 1ull) != 0;
-          tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
-          curInst = int32_t(w4.w);
-          inBlas = true;
-          ng = make_uint2(0u, 0x80000000u);  // bottom-level root; steps in the node phase below
+          // Object-space sphere test, conservative: the ray is turned away only when its line passes
+          // the centre at more than the radius plus a margin that outweighs the rounding of this
+          // computation (relative 1e-4 on r^2, 2e-5 on |origin - centre|^2: the closest-approach vector
+          // is a difference of two vectors of that size), or when the sphere lies behind the origin.
+          const float cx = oo.x - sph.x, cy = oo.y - sph.y, cz = oo.z - sph.z;
+          const float oc2 = cx * cx + cy * cy + cz * cz;
+          const float rp = sph.w * 1.0001f + 2e-5f * oc2 + 1e-30f;
+          bool enter = true;
+          if (oc2 > rp) {
+            const float A = od.x * od.x + od.y * od.y + od.z * od.z;
+            const float B = cx * od.x + cy * od.y + cz * od.z;
+            const float s = B * __frcp_rn_approx(A);
+            const float wx = cx - s * od.x, wy = cy - s * od.y, wz = cz - s * od.z;
+            enter = !(B > 0.0f) && !(wx * wx + wy * wy + wz * wz > rp);
+          }
+          if (enter) {
+            if (DETAIL) tc.entries++;
+            // what is left of this top-level node waits on the stack, below the bottom-level entries
+            if (ng.y & 0xff000000u) push(ng);
+            spBlas = sp;
+            r = setupRay(oo, od);
+            nodes = reinterpret_cast<const Node8*>(ptrs.x);
+            nonOpaque = (ptrs.y & 1ull) != 0;
+            tris = reinterpret_cast<const Tri48*>(ptrs.y & ~1ull);
+            curInst = int32_t(w4.w);
+            inBlas = true;
+            ng = make_uint2(0u, 0x80000000u);  // bottom-level root; steps in the node phase below
+          }
         }
       }
     }
