@@ -238,6 +238,116 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
 // st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
 // tlas: top-level layout -- every instance becomes an InstNode slot inside outNodes (st.slotOfInst),
 // so the array holds up to n real nodes plus n instance slots.
+// Binary hierarchy over the instance boxes by top-down binned SAH, on the host.  The top level has
+// at most a few thousand primitives, it is built when the instance set changes (per-frame motion is the
+// refit, which stays on the device), and its quality shows in every ray: on the articulated scene
+// (2 049 overlapping link boxes) the Morton-order hierarchy cost 9.1 top-level node visits per ray.
+// Output in the layout of k_lbvh_hierarchy: internal nodes 0..n-2 (root 0), child code >= 0 internal,
+// < 0 leaf ~position, range = positions covered, parent[] for internal nodes then leaves, and the
+// position -> primitive permutation in valsA.
+#define KF_TLAS_SAH_MAX 65536u
+static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
+  std::vector<float> box(size_t(6) * n);
+  KF_CUDA(ctx, cudaMemcpyAsync(box.data(), st.primBox.p, sizeof(float) * box.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> vals(n);
+  for (uint32_t i = 0; i < n; i++) vals[i] = i;
+  std::vector<int2> children(n - 1), range(n - 1);
+  std::vector<int> parent(size_t(2) * n - 1, -1);
+  struct Task { int node; uint32_t lo, hi; };
+  std::vector<Task> stack;
+  stack.push_back({0, 0u, n - 1});
+  int next = 1;
+  constexpr int BINS = 16;
+  auto area = [](const float* lo, const float* hi) {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+  };
+  while (!stack.empty()) {
+    const Task t = stack.back();
+    stack.pop_back();
+    const uint32_t cnt = t.hi - t.lo + 1;
+    // centroid bounds
+    float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
+    for (uint32_t k = t.lo; k <= t.hi; k++) {
+      const float* b = &box[size_t(6) * vals[k]];
+      for (int a = 0; a < 3; a++) {
+        const float c = 0.5f * (b[a] + b[3 + a]);
+        clo[a] = std::min(clo[a], c);
+        chi[a] = std::max(chi[a], c);
+      }
+    }
+    int bestAxis = -1, bestSplit = 0;
+    float bestCost = 3e38f;
+    for (int a = 0; a < 3 && cnt > 2; a++) {
+      const float ext = chi[a] - clo[a];
+      if (!(ext > 0.0f)) continue;
+      const float scale = float(BINS) / ext;
+      uint32_t bc[BINS] = {0};
+      float blo[BINS][3], bhi[BINS][3];
+      for (int b = 0; b < BINS; b++)
+        for (int k = 0; k < 3; k++) { blo[b][k] = 3e38f; bhi[b][k] = -3e38f; }
+      for (uint32_t k = t.lo; k <= t.hi; k++) {
+        const float* b = &box[size_t(6) * vals[k]];
+        const int bin = std::min(BINS - 1, std::max(0, int((0.5f * (b[a] + b[3 + a]) - clo[a]) * scale)));
+        bc[bin]++;
+        for (int c = 0; c < 3; c++) { blo[bin][c] = std::min(blo[bin][c], b[c]); bhi[bin][c] = std::max(bhi[bin][c], b[3 + c]); }
+      }
+      float rarea[BINS];
+      uint32_t rcnt[BINS];
+      float lo3[3] = {3e38f, 3e38f, 3e38f}, hi3[3] = {-3e38f, -3e38f, -3e38f};
+      uint32_t c = 0;
+      for (int b = BINS - 1; b > 0; b--) {
+        for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], blo[b][k]); hi3[k] = std::max(hi3[k], bhi[b][k]); }
+        c += bc[b];
+        rarea[b] = c ? area(lo3, hi3) : 0.0f;
+        rcnt[b] = c;
+      }
+      for (int k = 0; k < 3; k++) { lo3[k] = 3e38f; hi3[k] = -3e38f; }
+      c = 0;
+      for (int b = 0; b + 1 < BINS; b++) {  // split after bin b
+        for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], blo[b][k]); hi3[k] = std::max(hi3[k], bhi[b][k]); }
+        c += bc[b];
+        if (c == 0 || rcnt[b + 1] == 0) continue;
+        const float cost = area(lo3, hi3) * float(c) + rarea[b + 1] * float(rcnt[b + 1]);
+        if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
+      }
+    }
+    uint32_t mid;  // last position of the left part
+    if (bestAxis >= 0) {
+      const float scale = float(BINS) / (chi[bestAxis] - clo[bestAxis]);
+      auto it = std::stable_partition(vals.begin() + t.lo, vals.begin() + t.hi + 1, [&](uint32_t v) {
+        const float* b = &box[size_t(6) * v];
+        const int bin = std::min(BINS - 1, std::max(0, int((0.5f * (b[bestAxis] + b[3 + bestAxis]) - clo[bestAxis]) * scale)));
+        return bin <= bestSplit;
+      });
+      mid = uint32_t(it - vals.begin()) - 1;
+    } else {  // two primitives, or all centroids in one place: split in the middle
+      mid = t.lo + (cnt - 1) / 2;
+    }
+    const auto child = [&](uint32_t lo, uint32_t hi) {
+      if (lo == hi) {
+        parent[size_t(n) - 1 + lo] = t.node;
+        return ~int(lo);
+      }
+      const int idx = next++;
+      parent[size_t(idx)] = t.node;
+      stack.push_back({idx, lo, hi});
+      return idx;
+    };
+    const int l = child(t.lo, mid), r = child(mid + 1, t.hi);
+    children[size_t(t.node)] = make_int2(l, r);
+    range[size_t(t.node)] = make_int2(int(t.lo), int(t.hi));
+  }
+  KF_CUDA(ctx, cudaMemcpyAsync(st.children.p, children.data(), sizeof(int2) * (n - 1), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.range.p, range.data(), sizeof(int2) * (n - 1), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.parent.p, parent.data(), sizeof(int) * parent.size(), cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.valsA.p, vals.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  st.sortedVals = st.valsA.p;
+  return KFRT_OK;
+}
+
 // Scratch of a build over n primitives (DevBuf::ensure only ever grows a buffer).
 static int reserveBuild(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
   const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
@@ -287,11 +397,16 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     KF_CUDA(ctx, cudaGetLastError());
     return KFRT_OK;
   }
-  k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
-  int rc = radixSort(ctx, st, n);
-  if (rc) return rc;
-  k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
-                                                                 st.range.p, st.parent.p);
+  if (tlas && n <= KF_TLAS_SAH_MAX) {
+    int rc = sahTopLevelHierarchy(ctx, st, n);
+    if (rc) return rc;
+  } else {
+    k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
+    int rc = radixSort(ctx, st, n);
+    if (rc) return rc;
+    k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
+                                                                   st.range.p, st.parent.p);
+  }
   KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
   k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
                                                           st.sortedVals, st.nodeBox.p, st.flags.p);
