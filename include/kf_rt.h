@@ -156,7 +156,7 @@ typedef struct KfrtBvhStats {
   uint32_t nodeBytes;          /* bytes per wide node */
   uint32_t triangleBytes;      /* bytes per stored triangle */
   uint32_t instanceBytes;      /* bytes per instance record read on TLAS leaf entry */
-  uint32_t reserved;
+  uint32_t tlasRebuilds;       /* kfrtRefitTlas calls that rebuilt the top level instead (quality watch) */
 } KfrtBvhStats;
 
 typedef struct KfrtContext KfrtContext;
@@ -235,7 +235,9 @@ KFRT_API int kfrtSetInstances(KfrtContext* ctx, const KfrtInstance* instances, u
 /* Full top-level build over the current instances. */
 KFRT_API int kfrtBuildTlas(KfrtContext* ctx);
 /* Per-frame path: new column-major 4x4 transforms for the n current instances; topology of the
- * top-level tree is kept, boxes and inverse transforms are recomputed on the device. */
+ * top-level tree is kept, boxes and inverse transforms are recomputed on the device.  The call watches
+ * the quality of the refitted tree (area sum of its nodes, read back one call late) and runs the full
+ * build instead when it has degraded past 1.1x its value at build time. */
 KFRT_API int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n);
 KFRT_API int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out);
 

@@ -460,6 +460,18 @@ __global__ void k_lbvh_bounds(int n, const int2* __restrict__ children, const in
   }
 }
 
+// Sum of the surface areas of the binary internal nodes: the SAH cost of the hierarchy up to a
+// constant.  A refit keeps the topology, so this number says how far the moving instances have
+// stretched it since it was built.
+__global__ void k_area_sum(const float* __restrict__ nodeBox, uint32_t nInternal, float* __restrict__ out) {
+  float s = 0.0f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nInternal; i += gridDim.x * blockDim.x)
+    s += boxArea(loadBox(nodeBox + 6 * i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 // -------------------------------------------------------------------------------------------------
 // Wide-node emission
 // -------------------------------------------------------------------------------------------------

@@ -144,6 +144,13 @@ struct KfrtContext {
   uint32_t nTlasNodes = 0;
   bool blasBuilt = false, tlasBuilt = false;
   BuildState blasBuild, tlasBuild;
+  // quality watch of the refitted top level (see kfrtRefitTlas)
+  DevBuf<float> tlasArea;          // device scalar: area sum of the binary nodes after the last refit
+  float* tlasAreaHost = nullptr;   // pinned copy of it, filled asynchronously
+  cudaEvent_t tlasAreaReady = nullptr;
+  bool tlasAreaPending = false;
+  float tlasAreaAtBuild = 0.0f;
+  uint64_t tlasRebuilds = 0;
 
   // outputs
   uint32_t nCams = 0, width = 0, height = 0;
@@ -246,6 +253,7 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
 // < 0 leaf ~position, range = positions covered, parent[] for internal nodes then leaves, and the
 // position -> primitive permutation in valsA.
 #define KF_TLAS_SAH_MAX 65536u
+#define KF_TLAS_REBUILD_RATIO 1.1f
 static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
   std::vector<float> box(size_t(6) * n);
   KF_CUDA(ctx, cudaMemcpyAsync(box.data(), st.primBox.p, sizeof(float) * box.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -694,7 +702,9 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->geomTable.release(); ctx->blasInfo.release(); ctx->mats.release(); ctx->texTable.release();
   ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release(); ctx->alProjView.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
-  ctx->instRec.release(); ctx->instBoxInt.release(); ctx->tlasNodes.release();
+  ctx->instRec.release(); ctx->instBoxInt.release(); ctx->tlasNodes.release(); ctx->tlasArea.release();
+  if (ctx->tlasAreaHost) cudaFreeHost(ctx->tlasAreaHost);
+  if (ctx->tlasAreaReady) cudaEventDestroy(ctx->tlasAreaReady);
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
   ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
   ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
@@ -947,16 +957,9 @@ static int instanceRecords(KfrtContext* ctx) {
   return KFRT_OK;
 }
 
-int kfrtBuildTlas(KfrtContext* ctx) {
-  KF_CHECK_CTX(ctx);
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->blasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtBuildTlas before kfrtBuildBlas");
-  for (auto& g : ctx->geoms)
-    if (g.present && g.dirty) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "geometry uploaded after the last kfrtBuildBlas");
-  if (ctx->tablesDirty) {
-    int rc = uploadTables(ctx);
-    if (rc) return rc;
-  }
+// Top-level build from ctx->instHost (boxes, hierarchy, wide nodes, instance records) and the area
+// sum the later refits are compared with.
+static int buildTopLevel(KfrtContext* ctx) {
   const uint32_t n = uint32_t(ctx->instHost.size());
   int rc = instanceBoxes(ctx, true);
   if (rc) return rc;
@@ -972,10 +975,34 @@ int kfrtBuildTlas(KfrtContext* ctx) {
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasNodes.p, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice, ctx->stream));
   rc = instanceRecords(ctx);
   if (rc) return rc;
+  ctx->tlasAreaAtBuild = 0.0f;
+  ctx->tlasAreaPending = false;
+  if (n > 1) {
+    KF_CUDA(ctx, ctx->tlasArea.ensure(1));
+    if (!ctx->tlasAreaHost) KF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->tlasAreaHost), sizeof(float)));
+    if (!ctx->tlasAreaReady) KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tlasAreaReady, cudaEventDisableTiming));
+    KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasArea.p, 0, sizeof(float), ctx->stream));
+    k_area_sum<<<std::min<unsigned>(gridFor(n - 1, 256), 64u), 256, 0, ctx->stream>>>(st.nodeBox.p, n - 1, ctx->tlasArea.p);
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasAreaHost, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n > 1) ctx->tlasAreaAtBuild = *ctx->tlasAreaHost;
   ctx->nTlasNodes = st.nWide;
   ctx->tlasBuilt = true;
   return KFRT_OK;
+}
+
+int kfrtBuildTlas(KfrtContext* ctx) {
+  KF_CHECK_CTX(ctx);
+  KF_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->blasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtBuildTlas before kfrtBuildBlas");
+  for (auto& g : ctx->geoms)
+    if (g.present && g.dirty) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "geometry uploaded after the last kfrtBuildBlas");
+  if (ctx->tablesDirty) {
+    int rc = uploadTables(ctx);
+    if (rc) return rc;
+  }
+  return buildTopLevel(ctx);
 }
 
 int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
@@ -986,6 +1013,18 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   if (n == 0) return KFRT_OK;
   if (!transforms) KF_FAIL(ctx, KFRT_ERR_INVALID, "null transforms");
   for (uint32_t i = 0; i < n; i++) std::memcpy(ctx->instHost[i].transform, transforms + 16 * i, 64);
+  // A refit keeps the hierarchy of the last build; when the instances have moved far from where they
+  // were then, its boxes overlap and every ray pays (articulated scene: 6.3 top-level node visits per
+  // ray after a build, 38 after 40 frames of refits).  The area sum of the last refit (read back
+  // asynchronously, so one frame late and without a stall) decides: past KF_TLAS_REBUILD_RATIO times
+  // the value at build time the top level is built again from the new transforms.
+  if (ctx->tlasAreaPending && cudaEventQuery(ctx->tlasAreaReady) == cudaSuccess) {
+    ctx->tlasAreaPending = false;
+    if (ctx->tlasAreaAtBuild > 0.0f && *ctx->tlasAreaHost > KF_TLAS_REBUILD_RATIO * ctx->tlasAreaAtBuild) {
+      ctx->tlasRebuilds++;
+      return buildTopLevel(ctx);
+    }
+  }
   int rc = instanceBoxes(ctx, false);
   if (rc) return rc;
   BuildState& st = ctx->tlasBuild;
@@ -1002,6 +1041,13 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   }
   rc = instanceRecords(ctx);
   if (rc) return rc;
+  if (n > 1 && !ctx->tlasAreaPending && ctx->tlasAreaHost) {
+    KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasArea.p, 0, sizeof(float), ctx->stream));
+    k_area_sum<<<std::min<unsigned>(gridFor(n - 1, 256), 64u), 256, 0, ctx->stream>>>(st.nodeBox.p, n - 1, ctx->tlasArea.p);
+    KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasAreaHost, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaEventRecord(ctx->tlasAreaReady, ctx->stream));
+    ctx->tlasAreaPending = true;
+  }
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -1023,6 +1069,7 @@ int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   out->nodeBytes = sizeof(Node8);
   out->triangleBytes = sizeof(Tri48);
   out->instanceBytes = sizeof(InstNode);
+  out->tlasRebuilds = uint32_t(ctx->tlasRebuilds);
   return KFRT_OK;
 }
 

@@ -31,7 +31,7 @@ COUNTERS = np.dtype([("paths", "<u8"), ("extensionRays", "<u8"), ("shadowRays", 
 BVH_STATS = np.dtype([("blasCount", "<u4"), ("instanceCount", "<u4"), ("triangleCount", "<u8"),
                       ("instancedTriangles", "<u8"), ("blasNodeCount", "<u8"),
                       ("tlasNodeCount", "<u8"), ("nodeBytes", "<u4"), ("triangleBytes", "<u4"),
-                      ("instanceBytes", "<u4"), ("reserved", "<u4")])
+                      ("instanceBytes", "<u4"), ("tlasRebuilds", "<u4")])
 
 assert VERTEX.itemsize == 48 and MATERIAL.itemsize == 80 and INSTANCE.itemsize == 80
 assert CAMERA.itemsize == 320 and DIRECTIONAL_LIGHT.itemsize == 32

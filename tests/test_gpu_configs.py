@@ -83,6 +83,28 @@ def test_articulated_refit_through_facade(mods):
     r.close()
 
 
+def test_refit_quality_watch_rebuilds_without_changing_hits(mods):
+    """Forty frames of actor motion: kfrtRefitTlas rebuilds the top level when the refitted hierarchy has
+    stretched (area sum past 1.1x its value at build time); whichever of the two it did, the frame still
+    hits what the oracle hits for the same transforms."""
+    host, rt, oracle = mods
+    r = host.Renderer(device=0, accumulate=False)
+    r.load_scene("articulated", 64, 64, 1, 0, 6)
+    ctx = rt.Context(handle=r.device_context())
+    for frame in range(1, 41):
+        r.animate(frame)
+        r.clock_base = 7
+        r.run()
+    assert int(ctx.bvh_stats()["tlasRebuilds"]) >= 1
+    ws = r.wire_scene()
+    orc = oracle.Oracle()
+    ws.upload(orc)
+    ref = orc.render(np.array(ws.cams[:1]), ws.w, ws.h, ws.pc, clock_base=7)
+    assert np.array_equal(r.download_aux(wire.AUX_HIT_IDS, 0), ref["hit_ids"][0])
+    assert np.array_equal(r.download_aux(wire.AUX_HIT_T, 0).view(np.uint32), ref["hit_t"][0].view(np.uint32))
+    r.close()
+
+
 def test_accumulation_frames(mods):
     """frameCount semantics: accumulate on -> 0,1,2..; running mean equals the oracle's resolve."""
     host, rt, oracle = mods
