@@ -210,7 +210,7 @@ def run_reference(args, cfg, rank):
     r.load_scene(cfg["name"], cfg["width"], cfg["height"], cfg["spp"], cfg["depth"])
     ws = r.wire_scene()
     orc = oracle.Oracle()
-    ws.upload(orc)
+    orc.load(ws)
     cores = oracle.hardware_threads()
     sample_spp = max(1, min(args.cpu_sample_spp, cfg["spp"]))
     cams = np.array(ws.cams[:1])
@@ -437,7 +437,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         orc = oracle.Oracle()
-        ws.upload(orc)
+        orc.load(ws)
         cores = oracle.hardware_threads()
         sample_spp = max(1, min(args.cpu_sample_spp, spp))
         kind, cpu_render = cpu_arm()

@@ -44,7 +44,7 @@ KF_HD V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
 // Shading math only (radiance is compared with a tolerance, never bit for bit): one correctly rounded
 // reciprocal and three multiplies instead of three IEEE divisions (each a ~12-instruction sequence;
 // ncu showed this operator as 8.6 % of the shade kernel's instructions).  Within one ulp of a / s:
-// the parity margins of tools/parity_margin.py do not move (0.02 - 0.04 % of pixels beyond 1e-3).
+// the parity margins of tests/parity_margin.py do not move (0.02 - 0.04 % of pixels beyond 1e-3).
 // Going further -- rsqrt in normalize(), reciprocal quotients in the microfacet terms, SFU sine /
 // cosine -- buys another 7 % of the shade stage but puts 0.7 % of the pixels of the mirror-heavy
 // scenes beyond 1e-3 (limit 2 %), so it is not done.

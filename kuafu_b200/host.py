@@ -65,7 +65,8 @@ def _copy(ptr, nbytes, dtype):
 
 
 class WireSceneView:
-    """Packed wire buffers of a facade scene; `.upload(target)` feeds a kfrt Context or an Oracle."""
+    """Packed wire buffers of a facade scene; `.upload(ctx)` feeds a kfrt Context (the test-side oracle
+    reads the same view through `oracle.Oracle.load`)."""
 
     def __init__(self):
         self.geoms, self.textures, self.env = [], [], None
@@ -73,23 +74,20 @@ class WireSceneView:
         self.cams = []
         self.w = self.h = 0
 
-    def upload(self, target):
-        is_rt = hasattr(target, "upload_geometry")
-        if is_rt:  # Config limits of the facade renderer that packed this scene (kfcCreate)
-            target.set_limits(1025, 8192, 257, 4097)
+    def upload(self, ctx):
+        """Feeds a kuafu_b200.rt.Context (the C ABI) in the facade's own call order."""
+        ctx.set_limits(1025, 8192, 257, 4097)  # Config limits of the facade renderer that packed this scene
         for gi, (v, idx, mi, op, hide) in enumerate(self.geoms):
-            (target.upload_geometry if is_rt else target.set_geometry)(gi, v, idx, mi, op, hide)
-        (target.upload_materials if is_rt else target.set_materials)(self.mats)
+            ctx.upload_geometry(gi, v, idx, mi, op, hide)
+        ctx.upload_materials(self.mats)
         for ti, t in enumerate(self.textures):
-            (target.upload_texture if is_rt else target.set_texture)(ti, t)
+            ctx.upload_texture(ti, t)
         if self.env is not None:
-            (target.set_environment_cube if is_rt else target.set_env_cube)(self.env)
-        target.set_lights(self.dl, self.pl, self.al)
-        if is_rt:
-            target.build_blas()
-        target.set_instances(self.insts)
-        if is_rt:
-            target.build_tlas()
+            ctx.set_environment_cube(self.env)
+        ctx.set_lights(self.dl, self.pl, self.al)
+        ctx.build_blas()
+        ctx.set_instances(self.insts)
+        ctx.build_tlas()
 
     def n_tris(self):
         return int(sum(self.geoms[int(i["geometryIndex"])][1].size // 3 for i in self.insts))

@@ -92,6 +92,19 @@ class Oracle:
         if rc:
             raise RuntimeError(f"oracle {what} failed with code {rc}")
 
+    def load(self, view):
+        """Takes the packed wire buffers of a scene (kuafu_b200.host.WireSceneView or anything with the
+        same attributes): the oracle receives bit for bit what the C ABI receives."""
+        for gi, (v, idx, mi, op, hide) in enumerate(view.geoms):
+            self.set_geometry(gi, v, idx, mi, op, hide)
+        self.set_materials(view.mats)
+        for ti, t in enumerate(view.textures):
+            self.set_texture(ti, t)
+        if view.env is not None:
+            self.set_env_cube(view.env)
+        self.set_lights(view.dl, view.pl, view.al)
+        self.set_instances(view.insts)
+
     def set_geometry(self, index, vertices, indices, mat_index, opaque=True, hide=False):
         v = np.ascontiguousarray(vertices)
         assert v.dtype.itemsize == 48

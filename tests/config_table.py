@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measures the five BASELINE.json configs at full size through the facade (Kuafu::run on all recipe
 cameras, stage timers on) and prints one JSON line per config plus a markdown table.
-usage: python tools/config_table.py [--cpu] [names...]   (--cpu also times the oracle on a 1-spp sample)"""
+usage: python tests/config_table.py [--cpu] [names...]   (--cpu also times the oracle on a 1-spp sample)"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -38,7 +38,7 @@ for name, label in CONFIGS:
     if with_cpu:
         from oracle import oracle
         ws = r.wire_scene()
-        orc = oracle.Oracle(); ws.upload(orc)
+        orc = oracle.Oracle(); orc.load(ws)
         cores = oracle.hardware_threads()
         t0 = time.perf_counter()
         out = orc.render(np.array(ws.cams[:1], wire.CAMERA), ws.w, ws.h, ws.pc, 0, 1, clock_base=0, threads=cores)

@@ -37,7 +37,7 @@ def render_case(case):
     r.load_scene(recipe, w, h, spp, 0, scale)
     ws = r.wire_scene()
     orc = oracle.Oracle()
-    ws.upload(orc)
+    orc.load(ws)
     out = orc.render(np.array(ws.cams[:1]), ws.w, ws.h, ws.pc, clock_base=clock, threads=1)
     rgba = np.zeros_like(out["sum"])
     bgra = orc.resolve(out["sum"], rgba, spp, 0)
@@ -81,7 +81,7 @@ def converged_case(case):
     r.load_scene(recipe, w, h, spp, 0, scale)
     ws = r.wire_scene()
     orc = oracle.Oracle()
-    ws.upload(orc)
+    orc.load(ws)
     cams = np.array(ws.cams[:1])
     a = orc.render(cams, ws.w, ws.h, ws.pc, clock_base=ca)["sum"][0]
     b = orc.render(cams, ws.w, ws.h, ws.pc, clock_base=cb)["sum"][0]
@@ -100,7 +100,7 @@ def ref_case(case):
     r.load_scene(recipe, w, h, spp, 0, scale)
     ws = r.wire_scene()
     orc = oracle.Oracle()
-    ws.upload(orc)
+    orc.load(ws)
     out = ref.render(orc, np.array(ws.cams[:1]), ws.w, ws.h, ws.pc, clock_base=clock)
     return {"image": out["image"][0], "albedo": out["albedo"][0], "normal": out["normal"][0],
             "hit_ids": out["hit_ids"][0], "hit_t_bits": out["hit_t"][0].view(np.uint32),

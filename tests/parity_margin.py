@@ -15,7 +15,7 @@ for name, w, h, spp, scale in CASES:
     r.load_scene(name, w, h, spp, 0, scale)
     ws = r.wire_scene(); ws.cams = ws.cams[:1]
     ctx, orc = rt.Context(0), oracle.Oracle()
-    ws.upload(ctx); ws.upload(orc)
+    ws.upload(ctx); orc.load(ws)
     got, ref = parity.render_both(ws, ctx, orc, clock_base=0)
     parity.assert_hits_bit_exact(got, ref)
     st = parity.radiance_stats(got["sum"], ref["sum"], spp)

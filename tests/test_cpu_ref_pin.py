@@ -28,9 +28,17 @@ sys.path.insert(0, GOLDEN)
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built and no reference tree here")
 
 
+def _feed(orc, sc):
+    """A facade scene view goes through Oracle.load, a tests/pyscene.py scene through its own upload."""
+    if type(sc).__name__ == "WireSceneView":
+        orc.load(sc)
+    else:
+        sc.upload(orc)
+
+
 def both(sc, clock, brute=False, frame_count=0, prev=None):
     orc = oracle.Oracle()
-    sc.upload(orc)
+    _feed(orc, sc)
     cams = np.array(sc.cams)
     pc = np.array(sc.pc).copy()
     pc["frameCount"] = frame_count
@@ -135,7 +143,7 @@ def test_oracle_vs_frozen_shader_outputs(built, name, w, h, spp, scale, clock):
     g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
     sc = _config_scene(name, w, h, spp, scale)
     orc = oracle.Oracle()
-    sc.upload(orc)
+    _feed(orc, sc)
     a = orc.render(np.array(sc.cams), sc.w, sc.h, sc.pc, clock_base=clock)
     rgba = np.zeros_like(a["sum"])
     orc.resolve(a["sum"], rgba, spp, 0)

@@ -43,7 +43,7 @@ def test_config_parity_and_facade(mods, name, w, h, spp, scale):
     ctx = rt.Context(0)
     orc = oracle.Oracle()
     ws.upload(ctx)
-    ws.upload(orc)
+    orc.load(ws)
     got, ref = parity.render_both(ws, ctx, orc, clock_base=0)
     parity.assert_hits_bit_exact(got, ref)
     st = parity.radiance_stats(got["sum"], ref["sum"], spp)
@@ -69,7 +69,7 @@ def test_articulated_refit_through_facade(mods):
     r = host.Renderer(device=0, accumulate=False)
     r.load_scene("articulated", 96, 96, 1, 0, 6)
     orc = oracle.Oracle()
-    r.wire_scene().upload(orc)
+    orc.load(r.wire_scene())
     for frame in range(3):
         r.animate(frame)
         ws = r.wire_scene()
@@ -98,7 +98,7 @@ def test_refit_quality_watch_rebuilds_without_changing_hits(mods):
     assert int(ctx.bvh_stats()["tlasRebuilds"]) >= 1
     ws = r.wire_scene()
     orc = oracle.Oracle()
-    ws.upload(orc)
+    orc.load(ws)
     ref = orc.render(np.array(ws.cams[:1]), ws.w, ws.h, ws.pc, clock_base=7)
     assert np.array_equal(r.download_aux(wire.AUX_HIT_IDS, 0), ref["hit_ids"][0])
     assert np.array_equal(r.download_aux(wire.AUX_HIT_T, 0).view(np.uint32), ref["hit_t"][0].view(np.uint32))

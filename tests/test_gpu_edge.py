@@ -222,7 +222,7 @@ def test_imported_asset_parity(rt, orc_mod, tmp_path):
     assert ws.n_tris() == len(tris)
     ctx, orc = rt.Context(0), orc_mod.Oracle()
     ws.upload(ctx)
-    ws.upload(orc)
+    orc.load(ws)
     got, ref = parity.render_both(ws, ctx, orc, clock_base=2)
     parity.assert_hits_bit_exact(got, ref)
     assert (got["hit_ids"][..., 0] >= 0).mean() > 0.08     # the framing camera sees the asset
