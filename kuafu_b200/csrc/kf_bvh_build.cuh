@@ -543,7 +543,8 @@ struct CollapseArgs {
   int* wideBinary;            // wide node -> binary internal node it collapses
   int* wideMembers;           // 8 member codes per wide node (slot order), for refit
   uint32_t* counters;         // [0] wide nodes allocated, [1] leaf primitives allocated,
-                              // [2], [3] = [lo, hi) of the level being collapsed (k_next_level)
+                              // [2], [3] = [lo, hi) of the level being collapsed (k_next_level),
+                              // [4] = levels collapsed so far = depth of the wide tree
   uint32_t* slotOfInst;       // top level only: instance -> index of its InstNode in outNodes
 };
 
@@ -683,6 +684,7 @@ __global__ void k_collapse_level(CollapseArgs a) {
 }
 // The nodes allocated while collapsing level [lo, hi) form the next level.
 __global__ void k_next_level(uint32_t* counters) {
+  if (counters[3] > counters[2]) counters[4]++;  // a level that held nodes: the depth of the wide tree
   counters[2] = counters[3];
   counters[3] = counters[0];
 }

@@ -73,6 +73,7 @@ struct GeomHost {
   Tri48* tris = nullptr;
   ShadeTri* shade = nullptr;
   uint32_t nNodes = 0;
+  uint32_t depth = 0;  // levels of its wide tree
   float box[6] = {0, 0, 0, 0, 0, 0};
   void freeAll() {
     cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodesAlloc); cudaFree(tris); cudaFree(shade);
@@ -91,6 +92,7 @@ struct TexHost {
 struct BuildState {
   uint32_t n = 0;
   uint32_t nWide = 0;
+  uint32_t depth = 1;  // levels of the wide tree (the traversal stack holds at most one entry per level)
   DevBuf<float> primBox;
   DevBuf<int> sceneBox;
   DevBuf<uint64_t> keysA, keysB;
@@ -365,7 +367,7 @@ static int reserveBuild(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
   KF_CUDA(ctx, st.outPrim.ensure(n));
   KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * maxNodes));
   KF_CUDA(ctx, st.wideBinary.ensure(maxNodes));
-  KF_CUDA(ctx, st.counters.ensure(4));
+  KF_CUDA(ctx, st.counters.ensure(5));
   KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
   if (tlas) KF_CUDA(ctx, st.slotOfInst.ensure(std::max<uint32_t>(n, 1)));
   if ((tlas && n == 1) || (!tlas && n <= KF_LEAF_MAX)) return KFRT_OK;
@@ -395,6 +397,7 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, st.outNodes.p, st.wideBinary.p,
                                                       st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
     st.nWide = 2;
+    st.depth = 1;
     KF_CUDA(ctx, cudaGetLastError());
     return KFRT_OK;
   }
@@ -402,6 +405,7 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     k_single_leaf_root<<<1, 32, 0, ctx->stream>>>(int(n), st.primBox.p, st.outNodes.p, st.outPrim.p,
                                                   st.wideMembers.p, st.nodeBox.p);
     st.nWide = 1;
+    st.depth = 1;
     KF_CUDA(ctx, cudaGetLastError());
     return KFRT_OK;
   }
@@ -420,7 +424,7 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
                                                           st.sortedVals, st.nodeBox.p, st.flags.p);
   // collapse, one launch per level of the wide tree; the level ranges stay on the device and the
   // host looks at them once per batch of launches
-  const uint32_t init[4] = {1u, 0u, 0u, 1u};
+  const uint32_t init[5] = {1u, 0u, 0u, 1u, 0u};
   const int zero = 0;
   KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemcpyAsync(st.wideBinary.p, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -438,7 +442,7 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
   a.counters = st.counters.p;
   a.slotOfInst = tlas ? st.slotOfInst.p : nullptr;
   const unsigned grid = std::min<unsigned>(gridFor(maxNodes, 64), unsigned(ctx->numSMs) * 16u);
-  uint32_t lv[4] = {0, 0, 0, 1};
+  uint32_t lv[5] = {0, 0, 0, 1, 0};
   // a balanced 8-wide tree over n / 2 leaves has log8(n / 2) levels; LBVH trees are a little deeper
   int levels = 4;
   for (uint32_t m = n; m > 16; m >>= 3) levels++;
@@ -453,6 +457,7 @@ static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
     if (lv[0] > maxNodes) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
   }
   const uint32_t hi = lv[0];
+  st.depth = lv[4];
   st.nWide = hi;
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
@@ -502,6 +507,7 @@ static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
   k_write_shade_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, g.matIndex, nTris, g.shade);
   orderedBoxToFloat(ib, g.box);
   g.nNodes = st.nWide;
+  g.depth = st.depth;
   return KFRT_OK;
 }
 
@@ -971,6 +977,12 @@ static int buildTopLevel(KfrtContext* ctx) {
   BuildState& st = ctx->tlasBuild;
   rc = buildWideBvh(ctx, st, n, true);
   if (rc) return rc;
+  {  // the traversal stack holds at most one entry per level of the two trees a ray is in
+    uint32_t blasDepth = 0;
+    for (const auto& in : ctx->instHost) blasDepth = std::max(blasDepth, ctx->geoms[in.geometryIndex].depth);
+    if (st.depth + blasDepth > uint32_t(KF_STACK_SHARED + KF_STACK))
+      KF_FAIL(ctx, KFRT_ERR_LIMIT, "acceleration structure deeper than the traversal stack (KF_STACK)");
+  }
   KF_CUDA(ctx, ctx->tlasNodes.ensure(st.nWide));
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasNodes.p, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice, ctx->stream));
   rc = instanceRecords(ctx);
