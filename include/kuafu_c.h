@@ -50,6 +50,16 @@ KFC_API int kfcSetCamera(KfcRenderer* r, int camera);
 /* Kuafu::run() on the current camera / on all recipe cameras in one launch. */
 KFC_API int kfcRun(KfcRenderer* r);
 KFC_API int kfcRunAll(KfcRenderer* r);
+/* Camera-batch split across processes: Kuafu::cameraShard() and Kuafu::run() on the recipe
+ * cameras [begin, end) in one launch. */
+KFC_API int kfcCameraShard(int nCameras, int rank, int world, int* begin, int* end);
+KFC_API int kfcRunRange(KfcRenderer* r, int begin, int end);
+/* Scene::setEnvironmentMap(path) (a .ktx cube map) on the current scene. */
+KFC_API int kfcSetEnvironmentMap(KfcRenderer* r, const char* path);
+/* The facade's texture / cube-map file readers (image_io.hpp), for the reader tests: dimensions always,
+ * texels when dst holds at least width * height * 4 (x 6 for a cube) bytes. */
+KFC_API int kfcReadTexture(const char* path, uint32_t* width, uint32_t* height, uint8_t* dst, size_t capacity);
+KFC_API int kfcReadKtxCube(const char* path, uint32_t* size, uint8_t* dst, size_t capacity);
 /* spp sharding across processes: trace samples [begin,end) only; with deferResolve the caller sums
  * the KFRT_AUX_SUM32F device buffers of all ranks and then calls kfcResolve(). begin == end == 0
  * restores whole frames. */

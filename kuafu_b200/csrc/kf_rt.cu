@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -215,8 +216,19 @@ static void stageMark(KfrtContext* ctx, int stage) {
     }                                                                                          \
   } while (0)
 
-#define KF_CHECK_CTX(ctx) \
-  if (!(ctx)) return KFRT_ERR_INVALID
+// Every entry point makes the context's device current first: a context may be used from any one
+// thread at a time, and that thread may have another device current (two contexts on two GPUs in one
+// thread, or a context handed to a new thread); allocations, launches and copies below must land on
+// the device the context was created on.
+#define KF_CHECK_CTX(ctx)                                                                      \
+  do {                                                                                         \
+    if (!(ctx)) return KFRT_ERR_INVALID;                                                       \
+    cudaError_t _e = cudaSetDevice((ctx)->device);                                             \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(_e);                    \
+      return KFRT_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
 
 static inline unsigned gridFor(size_t n, unsigned block) { return unsigned((n + block - 1) / block); }
 
@@ -701,7 +713,6 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
 
 int kfrtDestroy(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
-  cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& g : ctx->geoms) g.freeAll();
   for (auto& t : ctx->texs) cudaFree(t.texels);
@@ -759,7 +770,6 @@ int kfrtUploadGeometry(KfrtContext* ctx, uint32_t geometryIndex, const KfrtVerte
   if (nMatIndex < nIndices / 3) KF_FAIL(ctx, KFRT_ERR_INVALID, "matIndex shorter than the primitive count");
   for (uint32_t i = 0; i < nIndices; i++)
     if (indices[i] >= nVertices) KF_FAIL(ctx, KFRT_ERR_INVALID, "vertex index out of range");
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->geoms.size() <= geometryIndex) ctx->geoms.resize(geometryIndex + 1);
   GeomHost& g = ctx->geoms[geometryIndex];
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -790,6 +800,7 @@ int kfrtClearGeometries(KfrtContext* ctx) {
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& g : ctx->geoms) g.freeAll();
   ctx->geoms.clear();
+  ctx->instHost.clear();  // they index the geometries that are gone; kfrtSetInstances brings new ones
   ctx->tablesDirty = true;
   ctx->blasBuilt = false;
   ctx->tlasBuilt = false;
@@ -892,7 +903,6 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
 
 int kfrtBuildBlas(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
   // size the build scratch once, for the largest geometry of this batch
   uint32_t maxTris = 0;
   for (auto& g : ctx->geoms)
@@ -967,6 +977,10 @@ static int instanceRecords(KfrtContext* ctx) {
 // sum the later refits are compared with.
 static int buildTopLevel(KfrtContext* ctx) {
   const uint32_t n = uint32_t(ctx->instHost.size());
+  // geometries may have been uploaded again (fewer of them, or one left empty) since kfrtSetInstances
+  for (const auto& in : ctx->instHost)
+    if (in.geometryIndex >= ctx->geoms.size() || !ctx->geoms[in.geometryIndex].present)
+      KF_FAIL(ctx, KFRT_ERR_INVALID, "an instance refers to a geometry that no longer exists; call kfrtSetInstances again");
   int rc = instanceBoxes(ctx, true);
   if (rc) return rc;
   if (n == 0) {
@@ -1006,7 +1020,6 @@ static int buildTopLevel(KfrtContext* ctx) {
 
 int kfrtBuildTlas(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->blasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtBuildTlas before kfrtBuildBlas");
   for (auto& g : ctx->geoms)
     if (g.present && g.dirty) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "geometry uploaded after the last kfrtBuildBlas");
@@ -1019,7 +1032,6 @@ int kfrtBuildTlas(KfrtContext* ctx) {
 
 int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   KF_CHECK_CTX(ctx);
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->tlasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtRefitTlas before kfrtBuildTlas");
   if (n != ctx->instHost.size()) KF_FAIL(ctx, KFRT_ERR_INVALID, "transform count differs from the instance count");
   if (n == 0) return KFRT_OK;
@@ -1100,6 +1112,17 @@ static int persistentGrid(KfrtContext* ctx, K kernel, int blockSize) {
   return ctx->numSMs * perSm;
 }
 
+// One traversal stage launch: closest hit (any == false) or occlusion.
+static void launchTrace(KfrtContext* ctx, const TraceArgs& te, bool any, bool detail) {
+  const int v = (any ? 2 : 0) + (detail ? 1 : 0);
+  switch (v) {
+    case 0: k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, ctx->stream>>>(te); break;
+    case 1: k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, ctx->stream>>>(te); break;
+    case 2: k_wf_trace<true, false><<<ctx->gridTrace[2], 128, 0, ctx->stream>>>(te); break;
+    default: k_wf_trace<true, true><<<ctx->gridTrace[3], 128, 0, ctx->stream>>>(te); break;
+  }
+}
+
 static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   const uint32_t tilesX = (ra.w + 7) / 8, tilesY = (ra.h + 3) / 4;
   const size_t slotsPerSample = size_t(ra.nCams) * tilesX * tilesY * 32;
@@ -1143,6 +1166,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow_resolve<true, false>, 128);
     ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow_resolve<true, true>, 128);
   }
+
   WfArgs a;
   a.sc = ra.sc;
   a.b.rayO = ctx->wfRayO.p;
@@ -1223,8 +1247,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.instPeriod = ctx->instPeriod;
       stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
       logBegin();
-      if (d) k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, st>>>(te);
-      else k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, st>>>(te);
+      launchTrace(ctx, te, false, d != 0);
       logEnd("closest", depth, te.count);
       stageMark(ctx, KFRT_STAGE_SHADE);
       switch (variant) {
@@ -1247,8 +1270,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
         ts.detailBase = 8;
         stageMark(ctx, KFRT_STAGE_TRACE_OCCLUSION);
         logBegin();
-        if (d) k_wf_trace<true, true><<<ctx->gridTrace[3], 128, 0, st>>>(ts);
-        else k_wf_trace<true, false><<<ctx->gridTrace[2], 128, 0, st>>>(ts);
+        launchTrace(ctx, ts, true, d != 0);
         logEnd("occlusion", depth, ts.count);
         stageMark(ctx, KFRT_STAGE_SHADOW_RESOLVE);
         switch (variant) {
@@ -1323,7 +1345,6 @@ static SceneDev sceneDev(KfrtContext* ctx) {
 int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, uint32_t width, uint32_t height,
                const KfrtPushConstants* pc, uint32_t sampleBegin, uint32_t sampleEnd, uint32_t clockBase) {
   KF_CHECK_CTX(ctx);
-  KF_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!cameras || !nCameras || !width || !height || !pc) KF_FAIL(ctx, KFRT_ERR_INVALID, "bad render arguments");
   if (sampleEnd < sampleBegin || sampleEnd > pc->sampleRatePerPixel)
     KF_FAIL(ctx, KFRT_ERR_INVALID, "sample range must lie inside [0, sampleRatePerPixel]");
@@ -1384,16 +1405,29 @@ int kfrtReduceNccl(KfrtContext* ctx, void* ncclComm, int root) {
   if (!ctx->rendered || !ncclComm) KF_FAIL(ctx, KFRT_ERR_INVALID, "kfrtReduceNccl needs a rendered frame and a communicator");
   typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
   typedef int (*ReduceFn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
-  static void* lib = nullptr;
+  // resolved once per process (contexts on several threads may get here together); a failed lookup
+  // is remembered with its reason and never leaves a half-filled table behind
+  static std::once_flag once;
   static AllReduceFn allReduce = nullptr;
   static ReduceFn reduce = nullptr;
-  if (!lib) {
-    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) KF_FAIL(ctx, KFRT_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
-    allReduce = reinterpret_cast<AllReduceFn>(dlsym(lib, "ncclAllReduce"));
-    reduce = reinterpret_cast<ReduceFn>(dlsym(lib, "ncclReduce"));
-    if (!allReduce || !reduce) KF_FAIL(ctx, KFRT_ERR_NCCL, "ncclAllReduce/ncclReduce not found");
-  }
+  static std::string loadError;
+  std::call_once(once, [] {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      const char* why = dlerror();
+      loadError = std::string("cannot load libnccl.so.2: ") + (why ? why : "unknown error");
+      return;
+    }
+    AllReduceFn ar = reinterpret_cast<AllReduceFn>(dlsym(lib, "ncclAllReduce"));
+    ReduceFn rd = reinterpret_cast<ReduceFn>(dlsym(lib, "ncclReduce"));
+    if (!ar || !rd) {
+      loadError = "ncclAllReduce/ncclReduce not found in libnccl.so.2";
+      return;
+    }
+    allReduce = ar;
+    reduce = rd;
+  });
+  if (!allReduce || !reduce) KF_FAIL(ctx, KFRT_ERR_NCCL, loadError);
   const size_t count = size_t(ctx->nCams) * ctx->width * ctx->height * 4;
   const int ncclFloat32 = 7, ncclSum = 0;
   int r = root < 0 ? allReduce(ctx->sum.p, ctx->sum.p, count, ncclFloat32, ncclSum, ncclComm, ctx->stream)

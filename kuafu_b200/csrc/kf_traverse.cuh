@@ -85,16 +85,12 @@ KF_D void fillMaskTables(MaskTables& t) {
   }
 }
 
-// Slab-tests the 8 quantised child boxes of `node`; returns the mask of the child slots the ray
-// MISSES (bit s = slot s; empty slots may report either, the caller masks with imask / triMask).
-KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, float tmin, float tmax,
-                            uint32_t& childBase, uint32_t& primBase, uint32_t& imask, uint32_t& triMask) {
-  const uint4* q = reinterpret_cast<const uint4*>(node);
-  const uint4 n0 = __ldg(q + 0);
-  const uint4 n1 = __ldg(q + 1);
-  const uint4 n2 = __ldg(q + 2);
-  const uint4 n3 = __ldg(q + 3);
-  const uint4 n4 = __ldg(q + 4);
+// Slab-tests the 8 quantised child boxes of a node given as its five 16-byte words; returns the mask
+// of the child slots the ray MISSES (bit s = slot s; empty slots may report either, the caller masks
+// with imask / triMask).
+KF_D uint32_t intersectNodeWords(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
+                                 const RaySetup& r, float tmin, float tmax, uint32_t& childBase,
+                                 uint32_t& primBase, uint32_t& imask, uint32_t& triMask) {
   childBase = n1.x;
   primBase = n1.y;
   triMask = n1.z;
@@ -140,6 +136,18 @@ KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, f
     miss |= ((z * 0x00204081u) >> 28) << (4 * h);
   }
   return miss;
+}
+
+// The same test with the node fetched here (5 x 16 B loads).
+KF_D uint32_t intersectNode(const Node8* __restrict__ node, const RaySetup& r, float tmin, float tmax,
+                            uint32_t& childBase, uint32_t& primBase, uint32_t& imask, uint32_t& triMask) {
+  const uint4* q = reinterpret_cast<const uint4*>(node);
+  const uint4 n0 = __ldg(q + 0);
+  const uint4 n1 = __ldg(q + 1);
+  const uint4 n2 = __ldg(q + 2);
+  const uint4 n3 = __ldg(q + 3);
+  const uint4 n4 = __ldg(q + 4);
+  return intersectNodeWords(n0, n1, n2, n3, n4, r, tmin, tmax, childBase, primBase, imask, triMask);
 }
 
 // Order-independent surrogate of the stochastic any-hit draw (reference PathTrace.rahit:30-48;

@@ -37,6 +37,11 @@ def load():
     lib.kfcSetCamera.argtypes = [vp, i32]
     lib.kfcRun.argtypes = [vp]
     lib.kfcRunAll.argtypes = [vp]
+    lib.kfcCameraShard.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    lib.kfcRunRange.argtypes = [vp, i32, i32]
+    lib.kfcSetEnvironmentMap.argtypes = [vp, C.c_char_p]
+    lib.kfcReadTexture.argtypes = [C.c_char_p, C.POINTER(u32), C.POINTER(u32), vp, sz]
+    lib.kfcReadKtxCube.argtypes = [C.c_char_p, C.POINTER(u32), vp, sz]
     lib.kfcSetSampleShard.argtypes = [vp, u32, u32, i32]
     lib.kfcResolve.argtypes = [vp]
     lib.kfcDownloadFrame.argtypes = [vp, i32, vp, sz]
@@ -62,6 +67,39 @@ def _copy(ptr, nbytes, dtype):
         return np.zeros(0, dtype)
     buf = (C.c_char * nbytes).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def camera_shard(n_cameras, rank, world):
+    """Kuafu::cameraShard: the contiguous camera range [begin, end) of `rank` among `world` processes."""
+    lib = load()
+    b, e = C.c_int(), C.c_int()
+    if lib.kfcCameraShard(n_cameras, rank, world, C.byref(b), C.byref(e)):
+        raise RuntimeError("kfcCameraShard: " + lib.kfcLastError().decode())
+    return b.value, e.value
+
+
+def read_texture(path):
+    """The facade's texture-file reader (PNG / PNM): (h, w, 4) uint8 RGBA."""
+    lib = load()
+    w, h = C.c_uint32(), C.c_uint32()
+    if lib.kfcReadTexture(str(path).encode(), C.byref(w), C.byref(h), None, 0):
+        raise RuntimeError("kfcReadTexture: " + lib.kfcLastError().decode())
+    out = np.empty((h.value, w.value, 4), "u1")
+    if lib.kfcReadTexture(str(path).encode(), C.byref(w), C.byref(h), out.ctypes.data_as(C.c_void_p), out.nbytes):
+        raise RuntimeError("kfcReadTexture: " + lib.kfcLastError().decode())
+    return out
+
+
+def read_ktx_cube(path):
+    """The facade's KTX1 cube-map reader: (6, size, size, 4) uint8 RGBA."""
+    lib = load()
+    s = C.c_uint32()
+    if lib.kfcReadKtxCube(str(path).encode(), C.byref(s), None, 0):
+        raise RuntimeError("kfcReadKtxCube: " + lib.kfcLastError().decode())
+    out = np.empty((6, s.value, s.value, 4), "u1")
+    if lib.kfcReadKtxCube(str(path).encode(), C.byref(s), out.ctypes.data_as(C.c_void_p), out.nbytes):
+        raise RuntimeError("kfcReadKtxCube: " + lib.kfcLastError().decode())
+    return out
 
 
 class WireSceneView:
@@ -132,6 +170,13 @@ class Renderer:
 
     def run_all(self):
         self._ck(self.lib.kfcRunAll(self.h), "kfcRunAll")
+
+    def run_range(self, begin, end):
+        """Kuafu::run() on the recipe cameras [begin, end) in one launch (camera-batch shard)."""
+        self._ck(self.lib.kfcRunRange(self.h, begin, end), "kfcRunRange")
+
+    def set_environment_map(self, path):
+        self._ck(self.lib.kfcSetEnvironmentMap(self.h, str(path).encode()), "kfcSetEnvironmentMap")
 
     def set_sample_shard(self, begin, end, defer_resolve=True):
         self._ck(self.lib.kfcSetSampleShard(self.h, begin, end, int(defer_resolve)), "kfcSetSampleShard")

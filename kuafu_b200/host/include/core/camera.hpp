@@ -22,6 +22,8 @@ class KUAFU_API Camera {
  public:
   Camera(const Camera&) = delete;
   Camera& operator=(const Camera&) = delete;
+  /// Unregisters from the context that still remembers this camera's last frame.
+  ~Camera();
 
   void update();
   void resetView();

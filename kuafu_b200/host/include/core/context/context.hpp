@@ -60,6 +60,7 @@ class KUAFU_API Context {
   void trace(const std::vector<Camera*>& cameras);
   void stashDisplacedFrames(const std::vector<Camera*>& next);
   void forgetCamera(Camera* camera);
+  void forgetScene(Scene* scene);
 
   KfrtContext* mRt = nullptr;
   uint32_t mClockBase = 0;

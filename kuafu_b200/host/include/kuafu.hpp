@@ -24,6 +24,11 @@ class KUAFU_API Kuafu {
   void run();
   /// Additive: render several cameras of the current scene in one launch (one TLAS refit).
   void run(const std::vector<Camera*>& cameras);
+  /// Additive (camera-batch split): the cameras process `rank` of `world` renders when a
+  /// batch of `nCameras` is split across GPUs -- a contiguous range [first, second), sizes differing by
+  /// at most one.  Every process holds the whole scene and refits its own top level once per run();
+  /// no collective is involved.
+  static std::pair<size_t, size_t> cameraShard(size_t nCameras, int rank, int world);
 
   [[nodiscard]] bool isRunning() const;
 

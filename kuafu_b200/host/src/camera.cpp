@@ -6,6 +6,10 @@
 #include "kf_rt.h"
 
 namespace kuafu {
+Camera::~Camera() {
+  if (mFrames.owner) mFrames.owner->forgetCamera(this);
+}
+
 Camera::Camera(int width, int height, const glm::vec3& position)
     : mWidth(width), mHeight(height), mPosition(position), mResetPosition(position), mPrevPosition(position) {
   mCx = mWidth * 0.5f;

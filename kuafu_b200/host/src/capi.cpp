@@ -1,5 +1,6 @@
 // Flat C view of the facade (include/kuafu_c.h).  Thin: every call forwards to the kuafu.hpp API.
 #include "kuafu_c.h"
+#include "image_io.hpp"
 
 #include "kf_rt.h"
 #include "scenes.hpp"
@@ -88,6 +89,44 @@ int kfcRun(KfcRenderer* r) {
 
 int kfcRunAll(KfcRenderer* r) {
   return guarded([&] { r->renderer->run(r->cameras); });
+}
+
+int kfcCameraShard(int nCameras, int rank, int world, int* begin, int* end) {
+  return guarded([&] {
+    if (nCameras < 0) throw std::runtime_error("kfcCameraShard: negative camera count");
+    const auto range = Kuafu::cameraShard(size_t(nCameras), rank, world);
+    *begin = int(range.first);
+    *end = int(range.second);
+  });
+}
+
+int kfcRunRange(KfcRenderer* r, int begin, int end) {
+  return guarded([&] {
+    if (begin < 0 || end < begin || size_t(end) > r->cameras.size()) throw std::runtime_error("kfcRunRange: bad camera range");
+    r->renderer->run(std::vector<Camera*>(r->cameras.begin() + begin, r->cameras.begin() + end));
+  });
+}
+
+int kfcSetEnvironmentMap(KfcRenderer* r, const char* path) {
+  return guarded([&] { r->renderer->getScene()->setEnvironmentMap(path); });
+}
+
+int kfcReadTexture(const char* path, uint32_t* width, uint32_t* height, uint8_t* dst, size_t capacity) {
+  return guarded([&] {
+    std::vector<uint8_t> rgba;
+    if (!io::loadTextureRGBA8(path, *width, *height, rgba)) throw std::runtime_error(std::string("cannot read texture ") + path);
+    if (dst && capacity >= rgba.size()) std::memcpy(dst, rgba.data(), rgba.size());
+  });
+}
+
+int kfcReadKtxCube(const char* path, uint32_t* size, uint8_t* dst, size_t capacity) {
+  return guarded([&] {
+    std::vector<uint8_t> faces[6];
+    if (!io::loadKtxCubeRGBA8(path, *size, faces)) throw std::runtime_error(std::string("cannot read cube map ") + path);
+    const size_t fb = size_t(*size) * *size * 4;
+    if (dst && capacity >= 6 * fb)
+      for (int f = 0; f < 6; f++) std::memcpy(dst + f * fb, faces[f].data(), fb);
+  });
 }
 
 int kfcSetSampleShard(KfcRenderer* r, uint32_t begin, uint32_t end, int deferResolve) {

@@ -8,6 +8,10 @@
 namespace kuafu {
 
 Context::~Context() {
+  // the cameras go first, while mLastCameras is still alive for their ~Camera -> forgetCamera()
+  mCurrentScene = nullptr;
+  mScenes.clear();
+  mLastCameras.clear();
   if (mRt) kfrtDestroy(mRt);
   mRt = nullptr;
 }
@@ -179,6 +183,13 @@ void Context::stashDisplacedFrames(const std::vector<Camera*>& next) {
 
 void Context::forgetCamera(Camera* camera) {
   mLastCameras.erase(std::remove(mLastCameras.begin(), mLastCameras.end(), camera), mLastCameras.end());
+}
+
+// A scene that is being destroyed: nothing of it may be looked at again (its cameras unregister
+// themselves in ~Camera; the uploaded-scene marker must not match a later scene at the same address).
+void Context::forgetScene(Scene* scene) {
+  if (mUploadedScene == scene) mUploadedScene = nullptr;
+  if (mCurrentScene == scene) mCurrentScene = nullptr;
 }
 
 void Context::trace(const std::vector<Camera*>& cameras) {

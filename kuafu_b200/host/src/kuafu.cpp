@@ -37,6 +37,12 @@ void Kuafu::run(const std::vector<Camera*>& cameras) {
   mContext.renderCameras(cameras);
 }
 
+std::pair<size_t, size_t> Kuafu::cameraShard(size_t nCameras, int rank, int world) {
+  KF_ASSERT(world > 0 && rank >= 0 && rank < world, "cameraShard: rank must lie in [0, world)");
+  const size_t r = size_t(rank), w = size_t(world);
+  return {nCameras * r / w, nCameras * (r + 1) / w};
+}
+
 std::vector<uint8_t> Kuafu::downloadLatestFrame(Camera* cam) {
   KF_ASSERT(cam, "Invalid call to Camera::downloadLatestFrame");
   return cam->downloadLatestFrame();
@@ -73,7 +79,7 @@ void Kuafu::removeScene(Scene* scene) {
   KF_ASSERT(scene, "Trying to remove an invalid scene!");
   auto it = std::find_if(mContext.mScenes.begin(), mContext.mScenes.end(), [scene](auto& s) { return s.get() == scene; });
   KF_ASSERT(it != mContext.mScenes.end(), "Scene does not belong to this renderer");
-  if (mContext.mCurrentScene == scene) mContext.mCurrentScene = nullptr;
+  mContext.forgetScene(scene);
   mContext.mScenes.erase(it);
 }
 }  // namespace kuafu
