@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native Kuafu path-tracing core.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode spp|cameras]
 
 Metric (BASELINE.json): Mrays/s and ms/frame at 1080p, 64 spp on config 3 (the ~1 M-triangle
 instanced PrincipledBSDF scene with textures and an environment cube, path depth 8, Russian roulette
@@ -10,7 +10,14 @@ shadow ray actually traced, counted on the device.
 
 N > 1 (one process per GPU under torchrun): the 64 samples of every pixel are split across ranks
 (replicated scene + BVH), the float4 sample sums are reduced onto rank 0 over NCCL and rank 0 runs the
-accumulate + encode epilogue -- strong scaling of one frame.
+accumulate + encode epilogue -- strong scaling of one frame.  The reduce is the C ABI's
+own collective (kfrtReduceNccl on a communicator from ncclCommInitRank), and after the timed steps rank 0
+renders the same frame alone and checks the sharded one against it (`frame_check`, at most 1 BGRA8 LSB).
+
+`--mode cameras` is the second natural shard (BASELINE config 5): the 64 cameras of the
+articulated scene are split across ranks (Kuafu::cameraShard), every rank refits its own top level once per
+frame, no collective on the data path; the per-rank BGRA8 frames are gathered onto rank 0 inside the e2e
+region.  Its line goes to profiles/, the driver's bench is the default mode.
 
 `value` is timed on the device with everything resident in HBM; `e2e` is the same frame through the
 public facade call (Kuafu::run + downloadLatestFrame) with host buffers, H2D/D2H inside the timed
@@ -44,6 +51,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="spp", choices=["spp", "cameras"])
     # debugging overrides (a run that uses them is not a bench value; they are echoed in `config`)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
@@ -126,14 +134,6 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
-
-
-class DevArray:
-    """__cuda_array_interface__ view of a kfrt device buffer, so torch can run a collective on it."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False),
-                                         "version": 3, "strides": None}
 
 
 def trace_closest_bytes(cnt, stats):
@@ -246,6 +246,149 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+class DevBytes:
+    """__cuda_array_interface__ view of a kfrt device buffer as bytes."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+CAMERA_CONFIG = {"name": "articulated", "width": 512, "height": 512, "spp": 32, "depth": 8}
+CAMERA_WORKLOAD = ("config 5: 64 chains x 32 links + floor = 2049 instances (10035202 instanced triangles), "
+                   "64 cameras x 512x512, 32 spp, path depth 8, every transform rewritten per frame -> one "
+                   "top-level refit per frame per GPU")
+
+
+def run_cameras(args, rank, world, local_rank):
+    """Camera-batch shard (SURVEY.md §8.6 way 2): cameras [b, e) of 64 per rank, replicated scene, one
+    refit per frame per rank (reference context.cpp:337-341: one update per run()), no collective on the
+    data path.  value: device time of Kuafu::run(range) (refit + trace + resolve), max over ranks; e2e: wall
+    clock of animate + run + gather of the BGRA8 frames onto rank 0 + copy to pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    from kuafu_b200 import host, rt, wire
+
+    cfg = dict(CAMERA_CONFIG)
+    if args.width:
+        cfg["width"] = args.width
+    if args.height:
+        cfg["height"] = args.height
+    if args.spp:
+        cfg["spp"] = args.spp
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    renderer = host.Renderer(device=local_rank, accumulate=False)
+    ncam = renderer.load_scene(cfg["name"], cfg["width"], cfg["height"], cfg["spp"], cfg["depth"])
+    b, e = host.camera_shard(ncam, rank, world)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = rt.Context(handle=renderer.device_context())
+    ctx.set_stream(stream.cuda_stream)
+    spp = cfg["spp"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, ev=None):
+        renderer.animate(i)
+        renderer.clock_base = i * (spp + 1)
+        if ev:
+            ev[0].record(stream)
+        renderer.run_range(b, e)
+        if ev:
+            ev[1].record(stream)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for i in range(args.warmup):
+        step(i)
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    my_rays, launches = 0, 0
+    for k in range(args.steps):
+        step(args.warmup + k, events[k])
+        c = ctx.counters()
+        my_rays += int(c["extensionRays"]) + int(c["shadowRays"])
+        launches += int(c["kernelLaunches"])
+        flush.zero_()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(events[k][0].elapsed_time(events[k][1]) for k in range(args.steps))
+    tot = torch.tensor([ms, float(my_rays)], dtype=torch.float64, device="cuda")
+    mx, sm = tot.clone(), tot.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    total_ms, rays_total = float(mx[0]), float(sm[1])
+    value = rays_total / (total_ms * 1e-3) / 1e6
+    stats = ctx.bvh_stats()
+
+    # e2e: frames of all ranks end up in pinned host memory on rank 0
+    frame_bytes = cfg["width"] * cfg["height"] * 4
+    per_rank = (e - b) * frame_bytes
+    assert world == 1 or all(host.camera_shard(ncam, k, world)[1] - host.camera_shard(ncam, k, world)[0] == e - b
+                             for k in range(world)), "camera mode wants equal shards"
+    pinned = torch.empty(ncam * frame_bytes, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+    gathered = [torch.empty(per_rank, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 and world > 1 else None
+    e2e_t, e2e_rays = 0.0, 0.0
+    for k in range(args.steps + 1):
+        i = 1000 + k
+        barrier()
+        t = time.perf_counter()
+        renderer.animate(i)
+        renderer.clock_base = i * (spp + 1)
+        renderer.run_range(b, e)
+        ptr, nbytes = ctx.device_buffer(wire.AUX_BGRA8)
+        mine = torch.as_tensor(DevBytes(ptr, nbytes), device="cuda")
+        if world > 1:
+            dist.gather(mine, gathered, dst=0)
+            if rank == 0:
+                for g, buf in enumerate(gathered):
+                    pinned[g * per_rank:(g + 1) * per_rank].copy_(buf, non_blocking=True)
+        else:
+            pinned.copy_(mine, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        c = ctx.counters()
+        r2 = torch.tensor([dt, float(int(c["extensionRays"]) + int(c["shadowRays"]))], dtype=torch.float64, device="cuda")
+        m2, s2 = r2.clone(), r2.clone()
+        if world > 1:
+            dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+        if k > 0:  # the first pass sizes the staging buffers
+            e2e_t += float(m2[0])
+            e2e_rays += float(s2[1])
+    if rank == 0:
+        assert int(pinned.view(-1, 4)[:, 3].min()) == 255  # every camera's frame arrived (alpha is 255 everywhere)
+        line = {
+            "metric": "Mrays/s (path tracing, config 5: 64 cameras x 512x512, 32 spp, per-frame TLAS refit)",
+            "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CAMERA_WORKLOAD, **cfg, "cameras": ncam, "parallelism": f"camera-shard x{world}",
+                       "cameras_per_gpu": e - b, "l2": "flushed between timed steps (512 MiB memset)",
+                       "triangles_instanced": int(stats["instancedTriangles"]), "instances": int(stats["instanceCount"])},
+            "per_gpu_mrays": value / world, "rays_per_step": rays_total / args.steps,
+            "tlas_rebuilds_rank0": int(stats["tlasRebuilds"]),
+            "e2e": {"value": e2e_rays / e2e_t / 1e6, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": 64 * int(stats["instanceCount"]) + (e - b) * 320 + 48 + 2592,
+                    "d2h_bytes_per_step": ncam * frame_bytes, "ms_per_step": e2e_t / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     cfg = effective_config(args)
@@ -256,17 +399,22 @@ def main():
     if args.impl == "reference":
         run_reference(args, cfg, rank)
         return
+    if args.mode == "cameras":
+        run_cameras(args, rank, world, local_rank)
+        return
 
     import torch
     import torch.distributed as dist
-    from kuafu_b200 import host, rt, wire
+    from kuafu_b200 import host, nccl, rt, wire
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = nccl.Communicator()  # raw ncclComm_t for kfrtReduceNccl
     if args.gpus != world and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
@@ -284,15 +432,15 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = rt.Context(handle=renderer.device_context())
     ctx.set_stream(stream.cuda_stream)
+    t_first = time.perf_counter()
     renderer.run()  # uploads, builds BLAS/TLAS, renders once
     torch.cuda.synchronize()
+    first_frame_ms = (time.perf_counter() - t_first) * 1e3  # geometry + texture upload, BLAS + TLAS build, first frame
     stats = ctx.bvh_stats()
     cams = np.array(ws.cams[:1], wire.CAMERA)
     pc = ws.pc
     n_pixels = cfg["width"] * cfg["height"]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    sum_ptr, sum_bytes = ctx.device_buffer(wire.AUX_SUM32F)
-    sum_t = torch.as_tensor(DevArray(sum_ptr, sum_bytes), device="cuda") if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -308,7 +456,7 @@ def main():
         if ev:
             ev[1].record(stream)
         if world > 1:
-            dist.reduce(sum_t, dst=0, op=dist.ReduceOp.SUM)
+            ctx.reduce_nccl(comm.handle, root=0)  # ncclReduce of the float4 sample sums, issued by the C ABI
         if rank == 0:
             ctx.resolve()
         if ev:
@@ -375,6 +523,20 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
+        # second line: what ncu measures as the binding limit of this kernel.  The BVH of the BASELINE
+        # scenes lives in L1/L2, so the byte line above is an accounting yardstick; the kernel is bound by
+        # instruction issue, and the useful fraction of the SM's SIMT issue capacity is
+        # issue-slot utilisation x active lanes per instruction / 32 (profiles/issue.json, from the ncu
+        # --set full capture of the same command; see profiles/README.md).
+        issue = None
+        ipath = os.path.join(ROOT, "profiles", "issue.json")
+        if os.path.exists(ipath):
+            with open(ipath) as f:
+                ij = json.load(f)
+            issue = {"bound": "issue", "achieved": ij["issue_active_pct"] / 100.0 * ij["lanes_per_inst"] / 32.0,
+                     "peak": 1.0, "unit": "fraction of SIMT lane-issue slots", "issue_active_pct": ij["issue_active_pct"],
+                     "lanes_per_inst": ij["lanes_per_inst"], "source": ij.get("source")}
+            issue["frac"] = issue["achieved"]
         dur = statistics.mean(render_ms) * 1e-3
         frame_achieved = abytes / dur / 1e9
         total_stage = sum(stage_ms.values()) or 1.0
@@ -388,7 +550,7 @@ def main():
                 # node step: 8 boxes x 6 slabs x 2 + min/max/compare; 45 per triangle test) against
                 # SMs x 128 lanes x 2 x clock.  Most of a node step is byte unpacking and mask logic,
                 # not flops, so this line sits far below the issue-slot utilisation ncu reports.
-                "alu": alu_line(kper, kbytes_per_launch, k_ms, stats),
+                "alu": alu_line(kper, kbytes_per_launch, k_ms, stats), "issue": issue,
                 "stages_ms_per_step": {n: v / args.steps for n, v in stage_ms.items() if v > 0},
                 "frame": {"achieved": frame_achieved, "frac": frame_achieved / peak,
                           "algorithmic_bytes_per_step": abytes, "bytes_per_ray": abytes / max(rays, 1),
@@ -411,7 +573,7 @@ def main():
         t = time.perf_counter()
         renderer.run()
         if world > 1:
-            dist.reduce(sum_t, dst=0, op=dist.ReduceOp.SUM)
+            ctx.reduce_nccl(comm.handle, root=0)
         if rank == 0:
             if world > 1:
                 renderer.resolve()
@@ -432,6 +594,25 @@ def main():
             e2e_t += dt
             e2e_rays += float(r[1])
     e2e_value = e2e_rays / e2e_t / 1e6
+
+    # ---- N > 1: the sharded, reduced and resolved frame against the same frame rendered by rank 0 alone
+    frame_check = None
+    if world > 1:
+        renderer.clock_base = 3000 * (spp + 1)
+        renderer.run()
+        ctx.reduce_nccl(comm.handle, root=0)
+        if rank == 0:
+            renderer.resolve()
+            sharded = renderer.download_frame(0).copy()
+            renderer.set_sample_shard(0, 0)
+            renderer.clock_base = 3000 * (spp + 1)
+            renderer.run()
+            alone = renderer.download_frame(0)
+            diff = np.abs(alone.astype(np.int16) - sharded.astype(np.int16))
+            frame_check = {"max_lsb": int(diff.max()), "bytes_differing": float((diff > 0).mean()),
+                           "against": "the same 64-spp frame rendered by rank 0 alone"}
+            assert frame_check["max_lsb"] <= 1, frame_check
+        barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -459,6 +640,7 @@ def main():
                        "instances": int(stats["instanceCount"])},
             "per_gpu_mrays": value / world,
             "rays_per_step": rays_total / args.steps,
+            "first_frame_ms": first_frame_ms, "frame_check": frame_check,
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t / args.steps * 1e3},
@@ -466,6 +648,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

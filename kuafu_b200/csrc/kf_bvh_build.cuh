@@ -460,6 +460,298 @@ __global__ void k_lbvh_bounds(int n, const int2* __restrict__ children, const in
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Top level: binary hierarchy over the instance boxes by top-down binned SAH, on the device.
+//
+// The top level has at most a few thousand primitives and its quality shows in every ray (on the
+// articulated scene, 2 049 overlapping link boxes, a Morton-order hierarchy costs 9.1 top-level node
+// visits per ray against 6.3 for this one), so it gets a real SAH sweep: 16 centroid bins per axis,
+// cost = area x count of both sides, the cheapest of the 45 candidate planes, stable partition; two
+// primitives, or centroids that all coincide, split in the middle.
+//
+// One block builds the whole tree level by level (no host round trip, no synchronisation of the
+// stream): per level every position finds its segment's centroid bounds and bins with atomics in
+// global scratch, one thread per segment sweeps the bins, a block-wide prefix sum over the "goes left"
+// flags gives every position its place in the stable partition, and a prefix sum over the segments
+// numbers the nodes and segments of the next level.  Output in the layout of k_lbvh_hierarchy: internal
+// nodes 0..n-2 (root 0), child code >= 0 internal, < 0 leaf ~position, range = positions covered,
+// parent[] for internal nodes then leaves, and the position -> primitive permutation in `vals`.
+// -------------------------------------------------------------------------------------------------
+#define KF_TLAS_BINS 16
+#define KF_TLAS_SAH_THREADS 1024
+
+struct TlasSahArgs {
+  uint32_t n;
+  const float* primBox;
+  uint32_t* vals;       // position -> primitive (result)
+  uint32_t* valsTmp;
+  int2* children;
+  int2* range;
+  int* parent;
+  uint32_t* segOf;      // [2][n]: segment of every position, this level / next level
+  int4* segs;           // [2][n / 2 + 1]: node, lo, hi, bin slot (segments of more than two primitives, else -1)
+  int* cbounds;         // [bin slots][6] centroid bounds, ordered ints
+  uint32_t* binCount;   // [bin slots][3][BINS]
+  int* binBox;          // [bin slots][3][BINS][6] ordered ints
+  int4* decision;       // [segments]: axis (-1: middle), split bin, nLeft, index of the first new segment
+  float2* decisionF;    // [segments]: centroid lower bound on the axis, bins / extent
+  uint32_t* pre;        // [n + 1] prefix sums over positions
+  uint32_t* segPre;     // [2][n / 2 + 2] prefix sums over segments: new segments, new bin slots
+};
+
+// Exclusive prefix sum of value(i), i in [0, total), into out[0..total] (out[total] = sum), by the
+// whole block.  `sh` holds 33 words.
+template <class F>
+KF_D void blockExclusiveScan(uint32_t total, uint32_t* __restrict__ out, uint32_t* sh, F value) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) sh[32] = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < total; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < total ? value(i) : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < nWarps ? sh[lane] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      sh[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t prefix = sh[32] + (warp > 0 ? sh[warp - 1] : 0u) + x - v;
+    if (i < total) out[i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) sh[32] = prefix + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[total] = sh[32];
+  __syncthreads();
+}
+
+KF_D float sahHalfArea(const float* lo, const float* hi) {
+  const float dx = csub(hi[0], lo[0]), dy = csub(hi[1], lo[1]), dz = csub(hi[2], lo[2]);
+  return cadd(cadd(cmul(dx, dy), cmul(dy, dz)), cmul(dz, dx));
+}
+KF_D int sahBin(float c, float clo, float scale) {
+  return min(KF_TLAS_BINS - 1, max(0, int(cmul(csub(c, clo), scale))));
+}
+
+__global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs a) {
+  __shared__ uint32_t sScan[33];
+  __shared__ uint32_t sCount[3];  // segments of this level, nodes allocated so far, bin slots of this level
+  const uint32_t n = a.n, T = blockDim.x, tid = threadIdx.x;
+  const uint32_t maxSeg = n / 2 + 1;
+  uint32_t* vals = a.vals;
+  uint32_t* valsOther = a.valsTmp;
+  uint32_t* segOf = a.segOf;
+  uint32_t* segOfNext = a.segOf + n;
+  int4* segs = a.segs;
+  int4* segsNext = a.segs + maxSeg;
+  for (uint32_t p = tid; p < n; p += T) {
+    vals[p] = p;
+    segOf[p] = 0;
+  }
+  if (tid == 0) {
+    segs[0] = make_int4(0, 0, int(n) - 1, n > 2 ? 0 : -1);
+    a.parent[0] = -1;
+    sCount[0] = 1;
+    sCount[1] = 1;
+    sCount[2] = n > 2 ? 1 : 0;
+  }
+  uint32_t* segPreBig = a.segPre + maxSeg + 1;
+  __syncthreads();
+  for (;;) {
+    const uint32_t nSeg = sCount[0], nBig = sCount[2];
+    if (nSeg == 0) break;
+    // ---- centroid bounds and bins of every segment with more than two primitives --------------
+    for (uint32_t i = tid; i < nBig * 6; i += T) a.cbounds[i] = floatToOrdered((i % 6) < 3 ? 3.0e38f : -3.0e38f);
+    for (uint32_t i = tid; i < nBig * 3 * KF_TLAS_BINS; i += T) a.binCount[i] = 0;
+    for (uint32_t i = tid; i < nBig * 3 * KF_TLAS_BINS * 6; i += T)
+      a.binBox[i] = floatToOrdered((i % 6) < 3 ? 3.0e38f : -3.0e38f);
+    __syncthreads();
+    for (uint32_t p = tid; p < n; p += T) {
+      const uint32_t s = segOf[p];
+      if (s == 0xffffffffu) continue;  // a finished leaf
+      const int slot = segs[s].w;
+      if (slot < 0) continue;
+      const float* b = a.primBox + 6 * size_t(vals[p]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float c = cmul(0.5f, cadd(b[k], b[3 + k]));
+        atomicMin(a.cbounds + 6 * slot + k, floatToOrdered(c));
+        atomicMax(a.cbounds + 6 * slot + 3 + k, floatToOrdered(c));
+      }
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n; p += T) {
+      const uint32_t s = segOf[p];
+      if (s == 0xffffffffu) continue;
+      const int slot = segs[s].w;
+      if (slot < 0) continue;
+      const float* b = a.primBox + 6 * size_t(vals[p]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float clo = orderedToFloat(a.cbounds[6 * slot + k]), chi = orderedToFloat(a.cbounds[6 * slot + 3 + k]);
+        const float ext = csub(chi, clo);
+        if (!(ext > 0.0f)) continue;
+        const int bin = sahBin(cmul(0.5f, cadd(b[k], b[3 + k])), clo, cdiv(float(KF_TLAS_BINS), ext));
+        const size_t bi = (size_t(slot) * 3 + k) * KF_TLAS_BINS + bin;
+        atomicAdd(a.binCount + bi, 1u);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          atomicMin(a.binBox + 6 * bi + c, floatToOrdered(b[c]));
+          atomicMax(a.binBox + 6 * bi + 3 + c, floatToOrdered(b[3 + c]));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one thread per segment: sweep the bins, keep the cheapest plane -------------------------
+    for (uint32_t s = tid; s < nSeg; s += T) {
+      const int4 sg = segs[s];
+      const int slot = sg.w;
+      int bestAxis = -1, bestSplit = 0;
+      float bestCost = 3.0e38f, bestClo = 0.0f, bestScale = 0.0f;
+      for (int k = 0; k < 3 && slot >= 0; k++) {
+        const float clo = orderedToFloat(a.cbounds[6 * slot + k]), chi = orderedToFloat(a.cbounds[6 * slot + 3 + k]);
+        const float ext = csub(chi, clo);
+        if (!(ext > 0.0f)) continue;
+        const size_t b0 = (size_t(slot) * 3 + k) * KF_TLAS_BINS;
+        float rarea[KF_TLAS_BINS];
+        uint32_t rcnt[KF_TLAS_BINS];
+        float lo3[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi3[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        uint32_t c = 0;
+        for (int b = KF_TLAS_BINS - 1; b > 0; b--) {
+          for (int q = 0; q < 3; q++) {
+            lo3[q] = fminf(lo3[q], orderedToFloat(a.binBox[6 * (b0 + b) + q]));
+            hi3[q] = fmaxf(hi3[q], orderedToFloat(a.binBox[6 * (b0 + b) + 3 + q]));
+          }
+          c += a.binCount[b0 + b];
+          rarea[b] = c ? sahHalfArea(lo3, hi3) : 0.0f;
+          rcnt[b] = c;
+        }
+        for (int q = 0; q < 3; q++) { lo3[q] = 3.0e38f; hi3[q] = -3.0e38f; }
+        c = 0;
+        for (int b = 0; b + 1 < KF_TLAS_BINS; b++) {  // split after bin b
+          for (int q = 0; q < 3; q++) {
+            lo3[q] = fminf(lo3[q], orderedToFloat(a.binBox[6 * (b0 + b) + q]));
+            hi3[q] = fmaxf(hi3[q], orderedToFloat(a.binBox[6 * (b0 + b) + 3 + q]));
+          }
+          c += a.binCount[b0 + b];
+          if (c == 0 || rcnt[b + 1] == 0) continue;
+          const float cost = cadd(cmul(sahHalfArea(lo3, hi3), float(c)), cmul(rarea[b + 1], float(rcnt[b + 1])));
+          if (cost < bestCost) {
+            bestCost = cost;
+            bestAxis = k;
+            bestSplit = b;
+            bestClo = clo;
+            bestScale = cdiv(float(KF_TLAS_BINS), ext);
+          }
+        }
+      }
+      a.decision[s] = make_int4(bestAxis, bestSplit, 0, 0);
+      a.decisionF[s] = make_float2(bestClo, bestScale);
+    }
+    __syncthreads();
+    // ---- stable partition: a prefix sum over the "goes left" flags of all positions ----------------
+    auto goesLeft = [&](uint32_t p) -> uint32_t {
+      const uint32_t s = segOf[p];
+      if (s == 0xffffffffu) return 0u;
+      const int4 sg = segs[s];
+      const int4 d = a.decision[s];
+      if (d.x < 0) return int(p) <= sg.y + (sg.z - sg.y) / 2 ? 1u : 0u;  // mid = lo + (cnt - 1) / 2
+      const float* b = a.primBox + 6 * size_t(vals[p]);
+      const float2 df = a.decisionF[s];
+      return sahBin(cmul(0.5f, cadd(b[d.x], b[3 + d.x])), df.x, df.y) <= d.y ? 1u : 0u;
+    };
+    blockExclusiveScan(n, a.pre, sScan, goesLeft);
+    // ---- children, nodes and segments of the next level ---------------------------------------------
+    auto newSegments = [&](uint32_t s) -> uint32_t {
+      const int4 sg = segs[s];
+      const uint32_t nLeft = a.pre[sg.z + 1] - a.pre[sg.y], cnt = uint32_t(sg.z - sg.y + 1);
+      return (nLeft > 1 ? 1u : 0u) + (cnt - nLeft > 1 ? 1u : 0u);
+    };
+    blockExclusiveScan(nSeg, a.segPre, sScan, newSegments);
+    auto newBinSlots = [&](uint32_t s) -> uint32_t {
+      const int4 sg = segs[s];
+      const uint32_t nLeft = a.pre[sg.z + 1] - a.pre[sg.y], cnt = uint32_t(sg.z - sg.y + 1);
+      return (nLeft > 2 ? 1u : 0u) + (cnt - nLeft > 2 ? 1u : 0u);
+    };
+    blockExclusiveScan(nSeg, segPreBig, sScan, newBinSlots);
+    const uint32_t nodeBase = sCount[1];
+    for (uint32_t s = tid; s < nSeg; s += T) {
+      const int4 sg = segs[s];
+      const int lo = sg.y, hi = sg.z;
+      const int nLeft = int(a.pre[hi + 1] - a.pre[lo]);
+      const int mid = lo + nLeft - 1;
+      uint32_t next = a.segPre[s], nextBig = segPreBig[s];
+      int4 d = a.decision[s];
+      d.z = nLeft;
+      d.w = int(next);
+      a.decision[s] = d;
+      int code[2];
+      const int clo2[2] = {lo, mid + 1}, chi2[2] = {mid, hi};
+      for (int side = 0; side < 2; side++) {
+        if (clo2[side] == chi2[side]) {
+          code[side] = ~clo2[side];
+          a.parent[size_t(n) - 1 + clo2[side]] = sg.x;
+        } else {
+          const int node = int(nodeBase + next);
+          code[side] = node;
+          a.parent[node] = sg.x;
+          segsNext[next] = make_int4(node, clo2[side], chi2[side], chi2[side] - clo2[side] + 1 > 2 ? int(nextBig++) : -1);
+          next++;
+        }
+      }
+      a.children[sg.x] = make_int2(code[0], code[1]);
+      a.range[sg.x] = make_int2(lo, hi);
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n; p += T) {
+      const uint32_t s = segOf[p];
+      if (s == 0xffffffffu) {
+        valsOther[p] = vals[p];
+        segOfNext[p] = 0xffffffffu;
+        continue;
+      }
+      const int4 sg = segs[s];
+      const int4 d = a.decision[s];
+      const uint32_t rankLeft = a.pre[p] - a.pre[sg.y];
+      const bool left = a.pre[p + 1] != a.pre[p];
+      const uint32_t cnt = uint32_t(sg.z - sg.y + 1), nLeft = uint32_t(d.z);
+      const uint32_t dst = left ? uint32_t(sg.y) + rankLeft : uint32_t(sg.y) + nLeft + (p - uint32_t(sg.y)) - rankLeft;
+      valsOther[dst] = vals[p];
+      uint32_t ns = 0xffffffffu;
+      if (left) {
+        if (nLeft > 1) ns = uint32_t(d.w);
+      } else if (cnt - nLeft > 1) {
+        ns = uint32_t(d.w) + (nLeft > 1 ? 1u : 0u);
+      }
+      segOfNext[dst] = ns;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sCount[1] = nodeBase + a.segPre[nSeg];
+      sCount[0] = a.segPre[nSeg];
+      sCount[2] = segPreBig[nSeg];
+    }
+    { uint32_t* t = vals; vals = valsOther; valsOther = t; }
+    { uint32_t* t = segOf; segOf = segOfNext; segOfNext = t; }
+    { int4* t = segs; segs = segsNext; segsNext = t; }
+    __syncthreads();
+  }
+  if (vals != a.vals)
+    for (uint32_t p = tid; p < n; p += T) a.vals[p] = vals[p];
+}
+
 // Sum of the surface areas of the binary internal nodes: the SAH cost of the hierarchy up to a
 // constant.  A refit keeps the topology, so this number says how far the moving instances have
 // stretched it since it was built.
@@ -689,6 +981,27 @@ __global__ void k_next_level(uint32_t* counters) {
   counters[3] = counters[0];
 }
 
+// Top level: the whole collapse in one launch of one block (a top level has at most a few thousand
+// nodes per level), so that a build needs no host round trip at all: the block walks the levels itself.
+// counters are read and written around L1 (the allocations of collapseNode are L2 atomics).
+#define KF_COLLAPSE_ALL_THREADS 512
+template <bool TLAS>
+__global__ void __launch_bounds__(KF_COLLAPSE_ALL_THREADS) k_collapse_all(CollapseArgs a) {
+  for (;;) {
+    const uint32_t lo = __ldcg(a.counters + 2), hi = __ldcg(a.counters + 3);
+    if (lo >= hi) break;
+    for (uint32_t w = lo + threadIdx.x; w < hi; w += blockDim.x) collapseNode<TLAS>(a, w);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __stcg(a.counters + 4, __ldcg(a.counters + 4) + 1u);
+      __stcg(a.counters + 2, hi);
+      __stcg(a.counters + 3, __ldcg(a.counters + 0));
+    }
+    __syncthreads();
+  }
+}
+
 // Root for n <= KF_LEAF_MAX primitives: one leaf child holding everything.
 __global__ void k_single_leaf_root(int n, const float* __restrict__ primBox, Node8* outNodes,
                                    uint32_t* outPrim, int* wideMembers, float* rootBox) {
@@ -735,11 +1048,12 @@ __global__ void k_single_instance_root(const float* __restrict__ primBox, Node8*
 
 // Refit: re-quantise every wide node from its members' freshly recomputed boxes.  wideBinary < 0
 // marks the InstNode slots of a top-level array, which k_instance_setup rewrites instead.
-__global__ void k_requantise(uint32_t nWide, const int* __restrict__ wideMembers, const int* __restrict__ wideBinary,
+// nWide: the number of wide nodes, on the device (the host only knows its bound).
+__global__ void k_requantise(const uint32_t* __restrict__ nWide, const int* __restrict__ wideMembers, const int* __restrict__ wideBinary,
                              const float* __restrict__ nodeBox, const float* __restrict__ primBox,
                              const uint32_t* __restrict__ vals, Node8* nodes, int singleLeafN) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nWide) return;
+  if (w >= *nWide) return;
   if (wideBinary && wideBinary[w] < 0) return;
   Box6 nb;
   boxReset(nb);

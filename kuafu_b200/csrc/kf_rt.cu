@@ -102,12 +102,19 @@ struct BuildState {
   DevBuf<int> parent, wideBinary, wideMembers;
   DevBuf<float> nodeBox;
   DevBuf<Node8> outNodes;
+  // scratch of the top-level SAH build (k_tlas_sah)
+  DevBuf<uint32_t> sahSegOf, sahBinCount, sahPre, sahSegPre;
+  DevBuf<int4> sahSegs, sahDecision;
+  DevBuf<float2> sahDecisionF;
+  DevBuf<int> sahBounds, sahBinBox;
   uint32_t* sortedVals = nullptr;  // valsA or valsB after the sort
   void release() {
     primBox.release(); sceneBox.release(); keysA.release(); keysB.release(); valsA.release();
     valsB.release(); hist.release(); flags.release(); outPrim.release(); counters.release();
     children.release(); range.release(); parent.release(); wideBinary.release();
     wideMembers.release(); nodeBox.release(); outNodes.release(); slotOfInst.release();
+    sahSegOf.release(); sahBinCount.release(); sahPre.release(); sahSegPre.release(); sahSegs.release();
+    sahDecision.release(); sahDecisionF.release(); sahBounds.release(); sahBinBox.release();
   }
 };
 
@@ -148,11 +155,17 @@ struct KfrtContext {
   bool blasBuilt = false, tlasBuilt = false;
   BuildState blasBuild, tlasBuild;
   // quality watch of the refitted top level (see kfrtRefitTlas)
-  DevBuf<float> tlasArea;          // device scalar: area sum of the binary nodes after the last refit
-  float* tlasAreaHost = nullptr;   // pinned copy of it, filled asynchronously
-  cudaEvent_t tlasAreaReady = nullptr;
-  bool tlasAreaPending = false;
+  DevBuf<float> tlasArea;          // device scalar: area sum of the binary nodes after the last build / refit
+  // what the host wants to know of a top-level build or refit comes back asynchronously, in pinned memory
+  struct TlasReadback {
+    float areaAtBuild, areaAfterRefit;
+    uint32_t nWide, depth;
+  };
+  TlasReadback* tlasRb = nullptr;
+  cudaEvent_t tlasBuildReady = nullptr, tlasAreaReady = nullptr;
+  bool tlasBuildPending = false, tlasAreaPending = false;
   float tlasAreaAtBuild = 0.0f;
+  uint32_t tlasBlasDepth = 0;  // deepest bottom level among the instances of the last build
   uint64_t tlasRebuilds = 0;
 
   // outputs
@@ -163,6 +176,15 @@ struct KfrtContext {
   DevBuf<float> hitT, depth;
   DevBuf<uchar4> bgra;
   DevBuf<unsigned long long> counters;
+  // The encoded frame starts its way to the host as soon as it is resolved: kfrtResolve queues an
+  // asynchronous copy of the BGRA8 buffer into pinned staging memory on a second stream, so that
+  // kfrtDownloadBGRA8 (== downloadLatestFrame) only waits for that copy and the next frame's kernels are
+  // not held up behind a pageable device -> host transfer.
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t resolvedEvent = nullptr, stagedEvent = nullptr;
+  uint8_t* bgraStage = nullptr;
+  size_t bgraStageCap = 0;
+  bool bgraStaged = false;
   KfrtPushConstants lastPc{};
   bool rendered = false;
   int detail = 0;
@@ -259,113 +281,41 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
 // st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
 // tlas: top-level layout -- every instance becomes an InstNode slot inside outNodes (st.slotOfInst),
 // so the array holds up to n real nodes plus n instance slots.
-// Binary hierarchy over the instance boxes by top-down binned SAH, on the host.  The top level has
-// at most a few thousand primitives, it is built when the instance set changes (per-frame motion is the
-// refit, which stays on the device), and its quality shows in every ray: on the articulated scene
-// (2 049 overlapping link boxes) the Morton-order hierarchy cost 9.1 top-level node visits per ray.
-// Output in the layout of k_lbvh_hierarchy: internal nodes 0..n-2 (root 0), child code >= 0 internal,
-// < 0 leaf ~position, range = positions covered, parent[] for internal nodes then leaves, and the
-// position -> primitive permutation in valsA.
+// Binary hierarchy over the instance boxes by top-down binned SAH: one launch of k_tlas_sah
+// (kf_bvh_build.cuh), no host round trip, no stream synchronisation.  It is built when the instance
+// set changes and when the refit watch trips (per-frame motion is the refit).
 #define KF_TLAS_SAH_MAX 65536u
 #define KF_TLAS_REBUILD_RATIO 1.1f
 static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
-  std::vector<float> box(size_t(6) * n);
-  KF_CUDA(ctx, cudaMemcpyAsync(box.data(), st.primBox.p, sizeof(float) * box.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<uint32_t> vals(n);
-  for (uint32_t i = 0; i < n; i++) vals[i] = i;
-  std::vector<int2> children(n - 1), range(n - 1);
-  std::vector<int> parent(size_t(2) * n - 1, -1);
-  struct Task { int node; uint32_t lo, hi; };
-  std::vector<Task> stack;
-  stack.push_back({0, 0u, n - 1});
-  int next = 1;
-  constexpr int BINS = 16;
-  auto area = [](const float* lo, const float* hi) {
-    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-    return dx * dy + dy * dz + dz * dx;
-  };
-  while (!stack.empty()) {
-    const Task t = stack.back();
-    stack.pop_back();
-    const uint32_t cnt = t.hi - t.lo + 1;
-    // centroid bounds
-    float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
-    for (uint32_t k = t.lo; k <= t.hi; k++) {
-      const float* b = &box[size_t(6) * vals[k]];
-      for (int a = 0; a < 3; a++) {
-        const float c = 0.5f * (b[a] + b[3 + a]);
-        clo[a] = std::min(clo[a], c);
-        chi[a] = std::max(chi[a], c);
-      }
-    }
-    int bestAxis = -1, bestSplit = 0;
-    float bestCost = 3e38f;
-    for (int a = 0; a < 3 && cnt > 2; a++) {
-      const float ext = chi[a] - clo[a];
-      if (!(ext > 0.0f)) continue;
-      const float scale = float(BINS) / ext;
-      uint32_t bc[BINS] = {0};
-      float blo[BINS][3], bhi[BINS][3];
-      for (int b = 0; b < BINS; b++)
-        for (int k = 0; k < 3; k++) { blo[b][k] = 3e38f; bhi[b][k] = -3e38f; }
-      for (uint32_t k = t.lo; k <= t.hi; k++) {
-        const float* b = &box[size_t(6) * vals[k]];
-        const int bin = std::min(BINS - 1, std::max(0, int((0.5f * (b[a] + b[3 + a]) - clo[a]) * scale)));
-        bc[bin]++;
-        for (int c = 0; c < 3; c++) { blo[bin][c] = std::min(blo[bin][c], b[c]); bhi[bin][c] = std::max(bhi[bin][c], b[3 + c]); }
-      }
-      float rarea[BINS];
-      uint32_t rcnt[BINS];
-      float lo3[3] = {3e38f, 3e38f, 3e38f}, hi3[3] = {-3e38f, -3e38f, -3e38f};
-      uint32_t c = 0;
-      for (int b = BINS - 1; b > 0; b--) {
-        for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], blo[b][k]); hi3[k] = std::max(hi3[k], bhi[b][k]); }
-        c += bc[b];
-        rarea[b] = c ? area(lo3, hi3) : 0.0f;
-        rcnt[b] = c;
-      }
-      for (int k = 0; k < 3; k++) { lo3[k] = 3e38f; hi3[k] = -3e38f; }
-      c = 0;
-      for (int b = 0; b + 1 < BINS; b++) {  // split after bin b
-        for (int k = 0; k < 3; k++) { lo3[k] = std::min(lo3[k], blo[b][k]); hi3[k] = std::max(hi3[k], bhi[b][k]); }
-        c += bc[b];
-        if (c == 0 || rcnt[b + 1] == 0) continue;
-        const float cost = area(lo3, hi3) * float(c) + rarea[b + 1] * float(rcnt[b + 1]);
-        if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
-      }
-    }
-    uint32_t mid;  // last position of the left part
-    if (bestAxis >= 0) {
-      const float scale = float(BINS) / (chi[bestAxis] - clo[bestAxis]);
-      auto it = std::stable_partition(vals.begin() + t.lo, vals.begin() + t.hi + 1, [&](uint32_t v) {
-        const float* b = &box[size_t(6) * v];
-        const int bin = std::min(BINS - 1, std::max(0, int((0.5f * (b[bestAxis] + b[3 + bestAxis]) - clo[bestAxis]) * scale)));
-        return bin <= bestSplit;
-      });
-      mid = uint32_t(it - vals.begin()) - 1;
-    } else {  // two primitives, or all centroids in one place: split in the middle
-      mid = t.lo + (cnt - 1) / 2;
-    }
-    const auto child = [&](uint32_t lo, uint32_t hi) {
-      if (lo == hi) {
-        parent[size_t(n) - 1 + lo] = t.node;
-        return ~int(lo);
-      }
-      const int idx = next++;
-      parent[size_t(idx)] = t.node;
-      stack.push_back({idx, lo, hi});
-      return idx;
-    };
-    const int l = child(t.lo, mid), r = child(mid + 1, t.hi);
-    children[size_t(t.node)] = make_int2(l, r);
-    range[size_t(t.node)] = make_int2(int(t.lo), int(t.hi));
-  }
-  KF_CUDA(ctx, cudaMemcpyAsync(st.children.p, children.data(), sizeof(int2) * (n - 1), cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(st.range.p, range.data(), sizeof(int2) * (n - 1), cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(st.parent.p, parent.data(), sizeof(int) * parent.size(), cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(st.valsA.p, vals.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  const size_t maxSeg = n / 2 + 1, maxSlots = n / 3 + 2;
+  KF_CUDA(ctx, st.sahSegOf.ensure(size_t(2) * n));
+  KF_CUDA(ctx, st.sahSegs.ensure(2 * maxSeg));
+  KF_CUDA(ctx, st.sahBounds.ensure(6 * maxSlots));
+  KF_CUDA(ctx, st.sahBinCount.ensure(3 * KF_TLAS_BINS * maxSlots));
+  KF_CUDA(ctx, st.sahBinBox.ensure(size_t(18) * KF_TLAS_BINS * maxSlots));
+  KF_CUDA(ctx, st.sahDecision.ensure(maxSeg));
+  KF_CUDA(ctx, st.sahDecisionF.ensure(maxSeg));
+  KF_CUDA(ctx, st.sahPre.ensure(size_t(n) + 1));
+  KF_CUDA(ctx, st.sahSegPre.ensure(2 * (maxSeg + 1)));
+  TlasSahArgs a;
+  a.n = n;
+  a.primBox = st.primBox.p;
+  a.vals = st.valsA.p;
+  a.valsTmp = st.valsB.p;
+  a.children = st.children.p;
+  a.range = st.range.p;
+  a.parent = st.parent.p;
+  a.segOf = st.sahSegOf.p;
+  a.segs = st.sahSegs.p;
+  a.cbounds = st.sahBounds.p;
+  a.binCount = st.sahBinCount.p;
+  a.binBox = st.sahBinBox.p;
+  a.decision = st.sahDecision.p;
+  a.decisionF = st.sahDecisionF.p;
+  a.pre = st.sahPre.p;
+  a.segPre = st.sahSegPre.p;
+  k_tlas_sah<<<1, KF_TLAS_SAH_THREADS, 0, ctx->stream>>>(a);
+  KF_CUDA(ctx, cudaGetLastError());
   st.sortedVals = st.valsA.p;
   return KFRT_OK;
 }
@@ -720,8 +670,9 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release(); ctx->alProjView.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
   ctx->instRec.release(); ctx->instBoxInt.release(); ctx->tlasNodes.release(); ctx->tlasArea.release();
-  if (ctx->tlasAreaHost) cudaFreeHost(ctx->tlasAreaHost);
+  if (ctx->tlasRb) cudaFreeHost(ctx->tlasRb);
   if (ctx->tlasAreaReady) cudaEventDestroy(ctx->tlasAreaReady);
+  if (ctx->tlasBuildReady) cudaEventDestroy(ctx->tlasBuildReady);
   ctx->blasBuild.release(); ctx->tlasBuild.release(); ctx->cams.release(); ctx->sum.release();
   ctx->rgba.release(); ctx->albedo.release(); ctx->normal.release(); ctx->hitIds.release();
   ctx->hitT.release(); ctx->depth.release(); ctx->bgra.release(); ctx->counters.release();
@@ -730,6 +681,13 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->wfHitB.release(); ctx->wfQueue0.release(); ctx->wfQueue1.release(); ctx->wfShadowQ0.release();
   ctx->wfShadowQ1.release(); ctx->wfCounts.release();
   for (cudaEvent_t e : ctx->stageEvents) cudaEventDestroy(e);
+  if (ctx->copyStream) {
+    cudaStreamSynchronize(ctx->copyStream);
+    cudaStreamDestroy(ctx->copyStream);
+  }
+  if (ctx->resolvedEvent) cudaEventDestroy(ctx->resolvedEvent);
+  if (ctx->stagedEvent) cudaEventDestroy(ctx->stagedEvent);
+  if (ctx->bgraStage) cudaFreeHost(ctx->bgraStage);
   if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
   delete ctx;
   return KFRT_OK;
@@ -973,9 +931,28 @@ static int instanceRecords(KfrtContext* ctx) {
   return KFRT_OK;
 }
 
-// Top-level build from ctx->instHost (boxes, hierarchy, wide nodes, instance records) and the area
-// sum the later refits are compared with.
-static int buildTopLevel(KfrtContext* ctx) {
+// What the last top-level build reported (node count, depth, area sum), once its readback has landed.
+static int consumeTlasBuild(KfrtContext* ctx) {
+  ctx->tlasBuildPending = false;
+  BuildState& st = ctx->tlasBuild;
+  st.nWide = ctx->tlasRb->nWide;
+  st.depth = ctx->tlasRb->depth;
+  ctx->nTlasNodes = st.nWide;
+  ctx->tlasAreaAtBuild = ctx->tlasRb->areaAtBuild;
+  // the traversal stack holds at most one entry per level of the two trees a ray is in
+  if (st.depth + ctx->tlasBlasDepth > uint32_t(KF_STACK_SHARED + KF_STACK)) {
+    ctx->tlasBuilt = false;
+    KF_FAIL(ctx, KFRT_ERR_LIMIT, "acceleration structure deeper than the traversal stack (KF_STACK)");
+  }
+  return KFRT_OK;
+}
+
+// Top-level build from ctx->instHost: instance boxes, binary hierarchy (binned SAH), 8-wide collapse with
+// every instance as a child slot, instance records, and the area sum the later refits are compared with.
+// Everything is enqueued on the stream; what the host wants back (node count, depth, area) arrives in
+// pinned memory behind an event.  wait: block until it has (kfrtBuildTlas); the rebuild the refit watch
+// triggers on the per-frame path does not wait.
+static int buildTopLevel(KfrtContext* ctx, bool wait) {
   const uint32_t n = uint32_t(ctx->instHost.size());
   // geometries may have been uploaded again (fewer of them, or one left empty) since kfrtSetInstances
   for (const auto& in : ctx->instHost)
@@ -983,38 +960,83 @@ static int buildTopLevel(KfrtContext* ctx) {
       KF_FAIL(ctx, KFRT_ERR_INVALID, "an instance refers to a geometry that no longer exists; call kfrtSetInstances again");
   int rc = instanceBoxes(ctx, true);
   if (rc) return rc;
+  ctx->tlasBuildPending = ctx->tlasAreaPending = false;
+  ctx->tlasAreaAtBuild = 0.0f;
   if (n == 0) {
     ctx->nTlasNodes = 0;
     ctx->tlasBuilt = true;
     return KFRT_OK;
   }
   BuildState& st = ctx->tlasBuild;
-  rc = buildWideBvh(ctx, st, n, true);
+  st.n = n;
+  rc = reserveBuild(ctx, st, n, true);
   if (rc) return rc;
-  {  // the traversal stack holds at most one entry per level of the two trees a ray is in
-    uint32_t blasDepth = 0;
-    for (const auto& in : ctx->instHost) blasDepth = std::max(blasDepth, ctx->geoms[in.geometryIndex].depth);
-    if (st.depth + blasDepth > uint32_t(KF_STACK_SHARED + KF_STACK))
-      KF_FAIL(ctx, KFRT_ERR_LIMIT, "acceleration structure deeper than the traversal stack (KF_STACK)");
+  const size_t maxNodes = size_t(2) * n + 1;
+  KF_CUDA(ctx, ctx->tlasNodes.ensure(maxNodes));
+  KF_CUDA(ctx, ctx->tlasArea.ensure(1));
+  if (!ctx->tlasRb) KF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->tlasRb), sizeof(*ctx->tlasRb)));
+  if (!ctx->tlasAreaReady) KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tlasAreaReady, cudaEventDisableTiming));
+  if (!ctx->tlasBuildReady) KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tlasBuildReady, cudaEventDisableTiming));
+  // the wide nodes are written where the traversal reads them; the InstNode slots among them come
+  // from k_instance_setup (instanceRecords) and get defined bytes until then
+  KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasNodes.p, 0, sizeof(Node8) * maxNodes, ctx->stream));
+  KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasArea.p, 0, sizeof(float), ctx->stream));
+  if (n == 1) {
+    k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, ctx->tlasNodes.p, st.wideBinary.p,
+                                                      st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
+    const uint32_t done[5] = {2u, 0u, 2u, 2u, 1u};
+    KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, done, sizeof(done), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    if (n <= KF_TLAS_SAH_MAX) {
+      rc = sahTopLevelHierarchy(ctx, st, n);
+      if (rc) return rc;
+    } else {
+      k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
+      rc = radixSort(ctx, st, n);
+      if (rc) return rc;
+      k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
+                                                                     st.range.p, st.parent.p);
+    }
+    KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
+    k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
+                                                            st.sortedVals, st.nodeBox.p, st.flags.p);
+    const uint32_t init[5] = {1u, 0u, 0u, 1u, 0u};
+    const int zero = 0;
+    KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(st.wideBinary.p, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CollapseArgs a;
+    a.n = int(n);
+    a.children = st.children.p;
+    a.range = st.range.p;
+    a.nodeBox = st.nodeBox.p;
+    a.primBox = st.primBox.p;
+    a.vals = st.sortedVals;
+    a.outNodes = ctx->tlasNodes.p;
+    a.outPrim = st.outPrim.p;
+    a.wideBinary = st.wideBinary.p;
+    a.wideMembers = st.wideMembers.p;
+    a.counters = st.counters.p;
+    a.slotOfInst = st.slotOfInst.p;
+    k_collapse_all<true><<<1, KF_COLLAPSE_ALL_THREADS, 0, ctx->stream>>>(a);
+    k_area_sum<<<std::min<unsigned>(gridFor(n - 1, 256), 64u), 256, 0, ctx->stream>>>(st.nodeBox.p, n - 1, ctx->tlasArea.p);
   }
-  KF_CUDA(ctx, ctx->tlasNodes.ensure(st.nWide));
-  KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasNodes.p, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice, ctx->stream));
   rc = instanceRecords(ctx);
   if (rc) return rc;
-  ctx->tlasAreaAtBuild = 0.0f;
-  ctx->tlasAreaPending = false;
-  if (n > 1) {
-    KF_CUDA(ctx, ctx->tlasArea.ensure(1));
-    if (!ctx->tlasAreaHost) KF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->tlasAreaHost), sizeof(float)));
-    if (!ctx->tlasAreaReady) KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tlasAreaReady, cudaEventDisableTiming));
-    KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasArea.p, 0, sizeof(float), ctx->stream));
-    k_area_sum<<<std::min<unsigned>(gridFor(n - 1, 256), 64u), 256, 0, ctx->stream>>>(st.nodeBox.p, n - 1, ctx->tlasArea.p);
-    KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasAreaHost, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (n > 1) ctx->tlasAreaAtBuild = *ctx->tlasAreaHost;
-  ctx->nTlasNodes = st.nWide;
+  KF_CUDA(ctx, cudaMemcpyAsync(&ctx->tlasRb->areaAtBuild, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(&ctx->tlasRb->nWide, st.counters.p + 0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(&ctx->tlasRb->depth, st.counters.p + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KF_CUDA(ctx, cudaEventRecord(ctx->tlasBuildReady, ctx->stream));
+  KF_CUDA(ctx, cudaGetLastError());
+  ctx->tlasBlasDepth = 0;
+  for (const auto& in : ctx->instHost) ctx->tlasBlasDepth = std::max(ctx->tlasBlasDepth, ctx->geoms[in.geometryIndex].depth);
+  ctx->tlasBuildPending = true;
+  ctx->nTlasNodes = uint32_t(maxNodes);  // its bound, until the readback lands
+  st.nWide = uint32_t(maxNodes);
   ctx->tlasBuilt = true;
+  if (wait) {
+    KF_CUDA(ctx, cudaEventSynchronize(ctx->tlasBuildReady));
+    return consumeTlasBuild(ctx);
+  }
   return KFRT_OK;
 }
 
@@ -1027,7 +1049,7 @@ int kfrtBuildTlas(KfrtContext* ctx) {
     int rc = uploadTables(ctx);
     if (rc) return rc;
   }
-  return buildTopLevel(ctx);
+  return buildTopLevel(ctx, true);
 }
 
 int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
@@ -1041,12 +1063,17 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   // were then, its boxes overlap and every ray pays (articulated scene: 6.3 top-level node visits per
   // ray after a build, 38 after 40 frames of refits).  The area sum of the last refit (read back
   // asynchronously, so one frame late and without a stall) decides: past KF_TLAS_REBUILD_RATIO times
-  // the value at build time the top level is built again from the new transforms.
+  // the value at build time the top level is built again from the new transforms -- enqueued like the
+  // refit it replaces, without waiting for it.
+  if (ctx->tlasBuildPending && cudaEventQuery(ctx->tlasBuildReady) == cudaSuccess) {
+    int rc = consumeTlasBuild(ctx);
+    if (rc) return rc;
+  }
   if (ctx->tlasAreaPending && cudaEventQuery(ctx->tlasAreaReady) == cudaSuccess) {
     ctx->tlasAreaPending = false;
-    if (ctx->tlasAreaAtBuild > 0.0f && *ctx->tlasAreaHost > KF_TLAS_REBUILD_RATIO * ctx->tlasAreaAtBuild) {
+    if (ctx->tlasAreaAtBuild > 0.0f && ctx->tlasRb->areaAfterRefit > KF_TLAS_REBUILD_RATIO * ctx->tlasAreaAtBuild) {
       ctx->tlasRebuilds++;
-      return buildTopLevel(ctx);
+      return buildTopLevel(ctx, false);
     }
   }
   int rc = instanceBoxes(ctx, false);
@@ -1056,19 +1083,19 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
     KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
     k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
                                                             st.sortedVals, st.nodeBox.p, st.flags.p);
-    k_requantise<<<gridFor(st.nWide, 128), 128, 0, ctx->stream>>>(st.nWide, st.wideMembers.p, st.wideBinary.p,
+    k_requantise<<<gridFor(st.nWide, 128), 128, 0, ctx->stream>>>(st.counters.p, st.wideMembers.p, st.wideBinary.p,
                                                                   st.nodeBox.p, st.primBox.p, st.sortedVals,
                                                                   ctx->tlasNodes.p, 0);
   } else {
-    k_requantise<<<1, 32, 0, ctx->stream>>>(1u, st.wideMembers.p, nullptr, st.nodeBox.p, st.primBox.p,
+    k_requantise<<<1, 32, 0, ctx->stream>>>(st.counters.p, st.wideMembers.p, nullptr, st.nodeBox.p, st.primBox.p,
                                             st.sortedVals, ctx->tlasNodes.p, 1);
   }
   rc = instanceRecords(ctx);
   if (rc) return rc;
-  if (n > 1 && !ctx->tlasAreaPending && ctx->tlasAreaHost) {
+  if (n > 1 && !ctx->tlasAreaPending && ctx->tlasRb) {
     KF_CUDA(ctx, cudaMemsetAsync(ctx->tlasArea.p, 0, sizeof(float), ctx->stream));
     k_area_sum<<<std::min<unsigned>(gridFor(n - 1, 256), 64u), 256, 0, ctx->stream>>>(st.nodeBox.p, n - 1, ctx->tlasArea.p);
-    KF_CUDA(ctx, cudaMemcpyAsync(ctx->tlasAreaHost, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(&ctx->tlasRb->areaAfterRefit, ctx->tlasArea.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     KF_CUDA(ctx, cudaEventRecord(ctx->tlasAreaReady, ctx->stream));
     ctx->tlasAreaPending = true;
   }
@@ -1079,6 +1106,11 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
 int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   KF_CHECK_CTX(ctx);
   if (!out) KF_FAIL(ctx, KFRT_ERR_INVALID, "null stats");
+  if (ctx->tlasBuildPending) {  // a rebuild on the refit path: its node count is still on its way
+    KF_CUDA(ctx, cudaEventSynchronize(ctx->tlasBuildReady));
+    int rc = consumeTlasBuild(ctx);
+    if (rc) return rc;
+  }
   std::memset(out, 0, sizeof(*out));
   for (auto& g : ctx->geoms) {
     if (!g.present) continue;
@@ -1312,6 +1344,8 @@ static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t 
   KF_CUDA(ctx, ctx->depth.ensure(np));
   KF_CUDA(ctx, ctx->bgra.ensure(np));
   if (changed) {
+    if (ctx->bgraStaged) KF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stagedEvent, 0));
+    ctx->bgraStaged = false;
     KF_CUDA(ctx, cudaMemsetAsync(ctx->rgba.p, 0, sizeof(float4) * np, ctx->stream));
     KF_CUDA(ctx, cudaMemsetAsync(ctx->bgra.p, 0, sizeof(uchar4) * np, ctx->stream));
   }
@@ -1390,11 +1424,31 @@ int kfrtResolve(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
   if (!ctx->rendered) KF_FAIL(ctx, KFRT_ERR_INVALID, "kfrtResolve before kfrtRender");
   const size_t np = size_t(ctx->nCams) * ctx->width * ctx->height;
+  if (!ctx->copyStream) {
+    KF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->resolvedEvent, cudaEventDisableTiming));
+    KF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stagedEvent, cudaEventDisableTiming));
+  }
+  // the staging copy of the previous frame reads the buffer this launch overwrites
+  if (ctx->bgraStaged) KF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stagedEvent, 0));
   k_resolve<<<gridFor(np, 256), 256, 0, ctx->stream>>>(ctx->sum.p, ctx->rgba.p, ctx->bgra.p, np,
                                                        ctx->lastPc.sampleRatePerPixel, ctx->lastPc.frameCount,
                                                        ctx->srgbThreshold.p);
   KF_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
+  if (ctx->bgraStageCap < np * 4) {
+    KF_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+    if (ctx->bgraStage) cudaFreeHost(ctx->bgraStage);
+    ctx->bgraStage = nullptr;
+    ctx->bgraStageCap = 0;
+    KF_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->bgraStage), np * 4));
+    ctx->bgraStageCap = np * 4;
+  }
+  KF_CUDA(ctx, cudaEventRecord(ctx->resolvedEvent, ctx->stream));
+  KF_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->resolvedEvent, 0));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->bgraStage, ctx->bgra.p, np * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+  KF_CUDA(ctx, cudaEventRecord(ctx->stagedEvent, ctx->copyStream));
+  ctx->bgraStaged = true;
   return KFRT_OK;
 }
 
@@ -1468,6 +1522,11 @@ int kfrtDownloadAux(KfrtContext* ctx, uint32_t camera, int kind, void* dst, size
   size_t pp = 0;
   if (bufferOf(ctx, kind, &p, &pp)) KF_FAIL(ctx, KFRT_ERR_INVALID, "unknown aux kind");
   if (nbytes != np * pp) KF_FAIL(ctx, KFRT_ERR_INVALID, "destination size mismatch");
+  if (kind == KFRT_AUX_BGRA8 && ctx->bgraStaged) {  // already on its way to (or in) pinned host memory
+    KF_CUDA(ctx, cudaEventSynchronize(ctx->stagedEvent));
+    std::memcpy(dst, ctx->bgraStage + camera * np * 4, nbytes);
+    return KFRT_OK;
+  }
   KF_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<char*>(p) + camera * np * pp, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return KFRT_OK;

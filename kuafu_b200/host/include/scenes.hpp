@@ -21,6 +21,8 @@ struct Recipe {
 ///   "active"       config 4  eActive (Example.hpp:479-645) with an IR dot-pattern projector, stereo pair
 ///   "articulated"  config 5  2048 link instances (64 chains x 32 links), 64 cameras, animate() per frame
 ///   "million_obj"  config 3 with every mesh written to a Wavefront file and read back by loadScene()
+///   "unique"       stress: config 3's layout with 204 un-instanced displaced blobs (1.0 M unique triangles)
+///   "unique10m"    stress: 1 000 un-instanced blobs of 10 000 triangles (10.0 M unique triangles)
 ///   "file:<path>"  the meshes of an asset file (.obj / .dae / .stl / .gltf / .glb), framed by one camera
 KUAFU_API std::vector<Camera*> load(Kuafu& renderer, const Recipe& recipe);
 
@@ -28,6 +30,8 @@ KUAFU_API std::vector<Camera*> load(Kuafu& renderer, const Recipe& recipe);
 KUAFU_API void animate(Kuafu& renderer, int frame);
 
 /// Displaced UV sphere standing in for resources/models/suzanne.dae (not shippable): same triangle
-/// count as the reference asset (251 904) at the default tessellation.
-KUAFU_API std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices = 512, uint32_t stacks = 247);
+/// count as the reference asset (251 904) at the default tessellation.  A non-zero seed gives the blob its
+/// own shape (the stress recipes with unique geometry).
+KUAFU_API std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices = 512, uint32_t stacks = 247,
+                                               uint32_t seed = 0);
 }  // namespace kuafu::scenes

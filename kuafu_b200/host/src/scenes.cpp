@@ -436,13 +436,18 @@ std::vector<Camera*> loadArticulated(Kuafu& r, const Recipe& rc) {  // config 5
 }
 }  // namespace
 
-std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices, uint32_t stacks) {
+std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices, uint32_t stacks, uint32_t seed) {
   auto g = createSphere(true, std::move(mat));  // registers the material; tessellation is replaced below
   g->vertices.clear();
   g->indices.clear();
   const float pi = glm::pi<float>();
-  auto radiusAt = [](float phi, float theta) {
-    return 1.0f + 0.18f * std::sin(3.0f * theta) * std::cos(2.0f * phi) + 0.07f * std::sin(9.0f * phi + 2.0f * theta) +
+  // seed 0 is the suzanne stand-in; any other seed shifts the phases and amplitudes of the displacement
+  // (theta terms keep integer frequencies so the surface closes on itself), so that no two blobs share a shape
+  Rng srng(seed * 2654435761u + 1u);
+  const float p0 = seed ? srng.range(0.f, 6.28f) : 0.0f, p1 = seed ? srng.range(0.f, 6.28f) : 0.0f;
+  const float a0 = seed ? srng.range(0.08f, 0.22f) : 0.18f, a1 = seed ? srng.range(0.03f, 0.09f) : 0.07f;
+  auto radiusAt = [=](float phi, float theta) {
+    return 1.0f + a0 * std::sin(3.0f * theta + p0) * std::cos(2.0f * phi) + a1 * std::sin(9.0f * phi + 2.0f * theta + p1) +
            0.12f * std::cos(2.0f * theta + 1.0f) * std::cos(phi);
   };
   for (uint32_t i = 1; i < stacks; ++i) {
@@ -476,6 +481,69 @@ std::shared_ptr<Geometry> createBlob(NiceMaterial mat, uint32_t slices, uint32_t
   g->path = "procedural:suzanne-substitute";
   g->recalculateNormals();
   return g;
+}
+
+// Stress recipes with UNIQUE geometry (no instancing): the layout of config 3, but every object is its
+// own displaced blob with its own bottom-level structure, so the traversal's working set is the whole
+// triangle count instead of 17 shared meshes -- what a scene of scanned assets looks like, and the case
+// where node and triangle fetches actually leave the 126 MB L2.
+//   "unique"     204 blobs x 4 900 triangles  =  1.0 M unique triangles (~ 0.15 GB of nodes, triangles, shading records)
+//   "unique10m"  1 000 blobs x 10 000 triangles = 10.0 M unique triangles (~ 1.5 GB)
+std::vector<Camera*> loadUnique(Kuafu& r, const Recipe& rc, int nDefault, uint32_t slices, uint32_t stacks) {
+  applyConfig(r, rc, 16, 8, true);
+  Scene* scene = r.getScene();
+  const int n = rc.scale > 0 ? rc.scale : nDefault;
+  int f = 1;
+  while (216 * f * f * f < n) f++;
+  Camera* cam = mainCamera(r, rc, 1920, 1080);
+  cam->setPosition(glm::vec3(-16.0F, -9.0F, 9.5F) * float(f));
+  cam->setFront({0.78F, 0.44F, -0.44F});
+  scene->setClearColor({0.6F, 0.7F, 0.9F, 1.0F});
+  auto sun = std::make_shared<DirectionalLight>();
+  sun->direction = {-1.0f, 0.6f, -1.5f};
+  sun->color = {1.0f, 0.95f, 0.85f};
+  sun->strength = 4;
+  sun->softness = 0.2f;
+  scene->setDirectionalLight(sun);
+  Rng texRng(2);
+  std::vector<std::shared_ptr<Geometry>> geoms;
+  NiceMaterial floorMat = material(glm::vec3(0.7f), 0.5f, 0.0f, 0.4f);
+  floorMat.diffuseTexPath = noiseTexture(texRng, "unique-floor", true);
+  auto floor = createYZPlane(true, floorMat);
+  geoms.push_back(floor);
+  // sixteen textured materials shared by all blobs (the reference loads the textures of every material
+  // entry, scene.cpp:314-413, so one entry per blob would exceed the texture limit)
+  const int nMaterials = 16;
+  std::vector<uint32_t> mats;
+  for (int m = 0; m < nMaterials; m++) {
+    NiceMaterial mat = material(glm::vec3(0.8f), 0.5f, (m % 4 == 1) ? 1.0f : 0.0f, 0.3f, 1.45f, (m % 4 == 2) ? 1.0f : 0.0f);
+    mat.diffuseTexPath = noiseTexture(texRng, "unique-d" + std::to_string(m), true);
+    mat.roughnessTexPath = noiseTexture(texRng, "unique-r" + std::to_string(m), false);
+    global::materials.push_back(mat);
+    mats.push_back(global::materialIndex++);
+  }
+  const NiceMaterial plain = material(glm::vec3(0.8f), 0.5f, 0.0f, 0.3f);
+  Rng rng(1);
+  std::vector<std::shared_ptr<GeometryInstance>> insts;
+  insts.push_back(instance(floor, trs({0.0F, 0.0F, -1.F}, 90.F, {0., -1., 0.}, glm::vec3(30.0F * float(f)))));
+  int placed = 0;
+  for (int k = 0; k < 3 * f && placed < n; k++)
+    for (int j = 0; j < 8 * f && placed < n; j++)
+      for (int i = 0; i < 9 * f && placed < n; i++) {
+        auto blob = createBlob(plain, slices, stacks, uint32_t(placed) + 1u);
+        blob->matIndex.assign(blob->matIndex.size(), mats[size_t(placed % nMaterials)]);
+        geoms.push_back(blob);
+        const glm::vec3 c((i - 4.5f * f + 0.5f) * 3.0f + rng.range(-0.6f, 0.6f), (j - 4.0f * f + 0.5f) * 3.0f + rng.range(-0.6f, 0.6f),
+                          0.2f + k * 2.8f + rng.range(-0.4f, 0.4f));
+        const float s = rng.range(0.7f, 1.25f);
+        const glm::vec3 axis(rng.range(-1.f, 1.f), rng.range(-1.f, 1.f), rng.range(0.1f, 1.f));
+        insts.push_back(instance(blob, trs(c, rng.range(0.f, 360.f), axis, {s, s * rng.range(0.8f, 1.2f), s})));
+        placed++;
+      }
+  scene->setGeometries(geoms);
+  scene->setGeometryInstances(insts);
+  skyCube(scene);
+  return {cam};
 }
 
 // "file:<path>": every mesh of an asset file (loadScene: .obj / .dae / .stl), one instance each, a
@@ -520,6 +588,8 @@ std::vector<Camera*> load(Kuafu& renderer, const Recipe& rc) {
   if (rc.name == "million") return loadMillion(renderer, rc);
   if (rc.name == "active") return loadActive(renderer, rc);
   if (rc.name == "articulated") return loadArticulated(renderer, rc);
+  if (rc.name == "unique") return loadUnique(renderer, rc, 204, 50, 50);
+  if (rc.name == "unique10m") return loadUnique(renderer, rc, 1000, 100, 51);
   throw std::runtime_error("unknown scene recipe: " + rc.name);
 }
 

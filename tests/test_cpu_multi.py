@@ -5,6 +5,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 import torch
@@ -53,6 +54,67 @@ def test_shard_ranges_partition():
             r = [shard(spp, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == spp
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+
+
+def _camera_worker(rank, world, port, q):
+    """Camera-batch shard on CPU: each rank asks the facade (Kuafu::cameraShard through the C view) for
+    its range of the config 5 camera batch and packs exactly those cameras; rank 0 checks that the
+    ranges tile the batch and that the packed cameras are the batch's own, in order."""
+    sys.path.insert(0, ROOT)
+    from kuafu_b200 import host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = host.Renderer(device=None)
+    ncam = r.load_scene("articulated", 32, 32, 1, 0, 7)  # 7 cameras: an uneven split
+    r.animate(2)
+    ws = r.wire_scene()
+    b, e = host.camera_shard(ncam, rank, world)
+    mine = np.stack([np.frombuffer(np.array(c).tobytes(), "u1") for c in ws.cams[b:e]]) if e > b else np.zeros((0, 320), "u1")
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (b, e))
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    tr = torch.from_numpy(np.ascontiguousarray(np.array(ws.insts)["transform"], np.float32).copy())
+    tr0 = tr.clone()
+    dist.broadcast(tr0, 0)
+    same_scene = bool(torch.equal(tr, tr0))  # every rank refits to the same transforms
+    if rank == 0:
+        tiled = ranges[0][0] == 0 and ranges[-1][1] == ncam and all(ranges[k][1] == ranges[k + 1][0] for k in range(world - 1))
+        sizes = [hi - lo for lo, hi in ranges]
+        even = max(sizes) - min(sizes) <= 1
+        whole = np.concatenate(parts)
+        allc = np.stack([np.frombuffer(np.array(c).tobytes(), "u1") for c in ws.cams])
+        q.put((tiled, even, bool(np.array_equal(whole, allc)), same_scene, ncam))
+    dist.barrier()
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_camera_shard():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_camera_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == (True, True, True, True, 7), res
+
+
+def test_camera_shard_ranges_partition():
+    from kuafu_b200 import host
+    for n in (0, 1, 7, 64):
+        for world in (1, 2, 3, 8):
+            r = [host.camera_shard(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+    with pytest.raises(RuntimeError):
+        host.camera_shard(8, 2, 2)
 
 
 def test_gloo_world2_spp_shard_reduce():

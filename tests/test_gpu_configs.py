@@ -3,7 +3,8 @@ the CPU oracle finishes in seconds.  Two checks per config:
   * the wire buffers the facade packs, fed to the raw C ABI and to the oracle, give bit-exact hit
     buffers and toleranced radiance;
   * Kuafu::run() + downloadLatestFrame() produce exactly what the raw C-ABI calls produce.
-Full-size runs are covered by size-independent properties in test_gpu_properties.py."""
+The configurations at their own size: test_gpu_fullsize.py (against the oracle) and the size-independent
+properties in test_gpu_edge.py."""
 import numpy as np
 import pytest
 

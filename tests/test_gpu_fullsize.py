@@ -1,0 +1,121 @@
+"""The BASELINE configurations at their own size, CUDA path vs the CPU oracle (north_star: "1-spp hit
+buffers bit-exact with the shader transcription"): config 3 on the very frame the headline number is
+quoted on (1920x1080, depth 8, sample 0 of 64), and config 5 at full scale (2 049 instances, 10 M
+instanced triangles, 64 cameras of 512^2) after a dozen frames of actor motion, so that the per-frame
+top-level refit *and* a rebuild triggered by the quality watch are both on the path that is checked.
+One oracle pass of these frames takes a few seconds on the box's host cores."""
+import numpy as np
+import pytest
+
+import parity
+from kuafu_b200 import wire
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    from kuafu_b200 import host, rt
+    from oracle import oracle
+    return host, rt, oracle
+
+
+def _facade_buffers(r, cam):
+    return {"hit_ids": r.download_aux(wire.AUX_HIT_IDS, cam)[None], "hit_t": r.download_aux(wire.AUX_HIT_T, cam)[None],
+            "depth": r.download_aux(wire.AUX_DEPTH, cam)[None], "albedo": r.download_aux(wire.AUX_ALBEDO32F, cam)[None],
+            "normal": r.download_aux(wire.AUX_NORMAL32F, cam)[None], "sum": r.download_aux(wire.AUX_SUM32F, cam)[None]}
+
+
+def test_config3_full_frame_hit_buffers(mods):
+    """bench.py's frame: config 3, 1920x1080, path depth 8, Russian roulette on -- sample 0 of every pixel
+    through the facade, against the oracle: instance / primitive ids, t bits and depth bits of all
+    2 073 600 primary hits, the albedo / normal hand-off buffers, ray counts and radiance."""
+    host, rt, oracle = mods
+    w, h = 1920, 1080
+    r = host.Renderer(device=0, accumulate=False)
+    r.load_scene("million", w, h, 1, 8)
+    ws = r.wire_scene()
+    assert ws.n_tris() == 999602 and int(ws.pc["maxPathDepth"]) == 8 and int(ws.pc["russianRoulette"]) == 1
+    r.clock_base = 5
+    r.run()
+    got = _facade_buffers(r, 0)
+    cnt = rt.Context(handle=r.device_context()).counters()
+    orc = oracle.Oracle()
+    orc.load(ws)
+    ref = orc.render(np.array(ws.cams[:1]), w, h, ws.pc, clock_base=5)
+    parity.assert_hits_bit_exact(got, ref)
+    assert (got["hit_ids"][..., 0] >= 0).mean() > 0.5
+    # one sample per pixel: a path whose discrete decisions flip on an ulp shows as a whole pixel
+    st = parity.radiance_stats(got["sum"], ref["sum"], 1)
+    assert st["frac_gt_1e-3"] < 0.02 and st["mean_rel_diff"] < 2e-3, st
+    assert int(cnt["paths"]) == ref["counters"]["paths"] == w * h
+    for k in ("extensionRays", "shadowRays", "extensionHits"):
+        assert abs(int(cnt[k]) - ref["counters"][k]) <= 0.02 * ref["counters"][k], (k, int(cnt[k]), ref["counters"][k])
+    r.close()
+
+
+def test_config5_full_scale_after_motion(mods):
+    """Config 5 as BASELINE words it: 64 chains x 32 links + floor = 2 049 instances (10 035 202 instanced
+    triangles), 64 cameras x 512x512, every transform rewritten each frame -> kfrtRefitTlas inside
+    Kuafu::run().  Twelve frames, all cameras in one launch; the last frame's cameras 0, 21 and 63 against
+    the oracle fed with that frame's transforms."""
+    host, rt, oracle = mods
+    r = host.Renderer(device=0, accumulate=False)
+    ncam = r.load_scene("articulated", 512, 512, 1)
+    assert ncam == 64
+    ws = r.wire_scene()
+    assert len(ws.insts) == 2049 and ws.n_tris() == 10035202
+    ctx = rt.Context(handle=r.device_context())
+    for frame in range(12):
+        r.animate(frame)
+        r.clock_base = 40 + frame
+        r.run_all()
+    stats = ctx.bvh_stats()
+    assert int(stats["instanceCount"]) == 2049
+    assert int(stats["tlasRebuilds"]) >= 1, "the quality watch never rebuilt the top level: only the refit path was checked"
+    ws = r.wire_scene()  # transforms of frame 11
+    orc = oracle.Oracle()
+    orc.load(ws)
+    for cam in (0, 21, 63):
+        ref = orc.render(np.array(ws.cams[cam:cam + 1]), 512, 512, ws.pc, clock_base=51)
+        got = _facade_buffers(r, cam)
+        parity.assert_hits_bit_exact(got, ref)
+        assert (got["hit_ids"][..., 0] >= 0).mean() > 0.2
+        st = parity.radiance_stats(got["sum"], ref["sum"], 1)
+        assert st["frac_gt_1e-3"] < 0.02 and st["mean_rel_diff"] < 2e-3, (cam, st)
+    r.close()
+
+
+def test_scene_reload_on_one_renderer(mods):
+    """load, render, load, render on one Renderer: the cameras of the first scene die with it
+    (Kuafu::removeScene) and the context must not look at them again (stale-camera regression)."""
+    host, rt, oracle = mods
+    r = host.Renderer(device=0, accumulate=False)
+    frames = []
+    for name, w, h in (("active", 96, 54), ("cornell", 64, 64), ("active", 96, 54)):
+        n = r.load_scene(name, w, h, 1)
+        r.clock_base = 3
+        r.run_all()
+        frames.append([r.download_frame(c).copy() for c in range(n)])
+        r.set_camera(0)
+        r.run()
+    assert len(frames[0]) == 2 and np.array_equal(frames[0][0], frames[2][0]) and np.array_equal(frames[0][1], frames[2][1])
+    assert frames[1][0].shape == (64, 64, 4)
+    r.close()
+
+
+def test_direct_abi_misuse_is_refused(mods):
+    """kfrtClearGeometries drops the instances that indexed the cleared geometries: building the top level
+    again without kfrtSetInstances gives an empty scene, never an out-of-bounds read."""
+    import pyscene
+    host, rt, oracle = mods
+    sc = pyscene.small_scene(seed=2, w=32, h=24, spp=1, depth=2, lights="dir")
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    ctx.clear_geometries()
+    ctx.build_blas()
+    ctx.build_tlas()
+    assert int(ctx.bvh_stats()["instanceCount"]) == 0
+    ctx.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, 1, 0)
+    assert (ctx.download_aux(wire.AUX_HIT_IDS) == -1).all()
+    ctx.close()

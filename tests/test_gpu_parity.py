@@ -55,6 +55,26 @@ def test_small_scene_hits_and_radiance(rt, orc_mod, lights):
     ctx.close()
 
 
+@pytest.mark.parametrize("fov_deg,softness", [(150.0, 0.0), (40.0, 0.0), (40.0, 0.3)])
+def test_spot_light_without_texture(rt, orc_mod, fov_deg, softness):
+    """The reference's "spot" light is an ActiveLight without a projector texture (scene.cpp:407,
+    PathTrace.rchit:262-316 with texID < 0): cone test only, no projection, colour = rgb.  The narrow
+    cone leaves most of the scene outside it (lights that fail the cone test draw no further random
+    numbers), the soft one perturbs the light position first."""
+    sc = pyscene.small_scene(seed=2, w=128, h=96, spp=2, depth=6, lights="active", textures=False)
+    assert int(sc.al["sftp"][0][2]) == -1
+    sc.al["sftp"][0][0] = softness
+    sc.al["sftp"][0][1] = np.radians(fov_deg)
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc)
+    parity.assert_hits_bit_exact(got, ref)
+    _check_radiance(got, ref, 2)
+    assert ref["counters"]["shadowRays"] > 0
+    for k in ("extensionRays", "shadowRays", "extensionHits"):
+        assert abs(got["counters"][k] - ref["counters"][k]) <= 0.02 * max(ref["counters"][k], 1), (k, got["counters"], ref["counters"])
+    ctx.close()
+
+
 def test_brute_force_oracle_agrees(rt, orc_mod):
     """BVH layout must not change the answer: GPU (8-wide LBVH) == oracle brute force over all triangles."""
     sc = pyscene.small_scene(seed=5, w=64, h=48, spp=1, depth=3, lights="dir", stacks=6, slices=8)
