@@ -85,31 +85,6 @@ KF_D float orderedToFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fff
 // -------------------------------------------------------------------------------------------------
 // primitive setup
 // -------------------------------------------------------------------------------------------------
-// One thread per triangle: padded box + contribution to the scene box.
-__global__ void k_tri_boxes(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
-                            uint32_t nTris, float* __restrict__ primBox, int* __restrict__ sceneBox) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nTris) return;
-  Box6 b;
-  boxReset(b);
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    const float* p = verts[idx[3 * t + c]].pos;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      b.lo[k] = fminf(b.lo[k], p[k]);
-      b.hi[k] = fmaxf(b.hi[k], p[k]);
-    }
-  }
-  boxPad(b);
-  storeBox(primBox + 6 * t, b);
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    atomicMin(sceneBox + k, floatToOrdered(b.lo[k]));
-    atomicMax(sceneBox + 3 + k, floatToOrdered(b.hi[k]));
-  }
-}
-
 __global__ void k_init_scene_box(int* sceneBox) {
   if (threadIdx.x < 3) sceneBox[threadIdx.x] = floatToOrdered(3.0e38f);
   else if (threadIdx.x < 6) sceneBox[threadIdx.x] = floatToOrdered(-3.0e38f);
@@ -864,6 +839,7 @@ KF_D void collapseNode(const CollapseArgs& a, uint32_t w) {
     for (int s = 0; s < 8; s++) a.wideMembers[8 * w + s] = KF_MEMBER_EMPTY;
     return;
   }
+  // (wideMembers is what a refit re-quantises from: the top level keeps it, bottom levels are never refitted)
   int mem[8];
   int m = 0;
   {
@@ -936,7 +912,7 @@ KF_D void collapseNode(const CollapseArgs& a, uint32_t w) {
   uint32_t imask = 0, ci = 0, po = 0, realNodes = 0, triMask = 0;
   for (int s = 0; s < 8; s++) {
     const int code = slotMem[s];
-    a.wideMembers[8 * w + s] = code;
+    if (TLAS) a.wideMembers[8 * w + s] = code;
     if (code == KF_MEMBER_EMPTY) continue;
     const int cnt = memberCount(code, a.range);
     if (cnt > LEAF_MAX) {
@@ -965,22 +941,6 @@ KF_D void collapseNode(const CollapseArgs& a, uint32_t w) {
   a.outNodes[w] = nd;
 }
 
-// The level's range [lo, hi) is read from the device (a.counters[2..3]) and the grid strides over
-// it, so the host enqueues level after level without knowing their widths: no device -> host round
-// trip per level (the first version had one, and the build was bound by them).
-template <bool TLAS>
-__global__ void k_collapse_level(CollapseArgs a) {
-  const uint32_t lo = a.counters[2], hi = a.counters[3];
-  for (uint32_t w = lo + blockIdx.x * blockDim.x + threadIdx.x; w < hi; w += gridDim.x * blockDim.x)
-    collapseNode<TLAS>(a, w);
-}
-// The nodes allocated while collapsing level [lo, hi) form the next level.
-__global__ void k_next_level(uint32_t* counters) {
-  if (counters[3] > counters[2]) counters[4]++;  // a level that held nodes: the depth of the wide tree
-  counters[2] = counters[3];
-  counters[3] = counters[0];
-}
-
 // Top level: the whole collapse in one launch of one block (a top level has at most a few thousand
 // nodes per level), so that a build needs no host round trip at all: the block walks the levels itself.
 // counters are read and written around L1 (the allocations of collapseNode are L2 atomics).
@@ -1000,28 +960,6 @@ __global__ void __launch_bounds__(KF_COLLAPSE_ALL_THREADS) k_collapse_all(Collap
     }
     __syncthreads();
   }
-}
-
-// Root for n <= KF_LEAF_MAX primitives: one leaf child holding everything.
-__global__ void k_single_leaf_root(int n, const float* __restrict__ primBox, Node8* outNodes,
-                                   uint32_t* outPrim, int* wideMembers, float* rootBox) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Box6 nb;
-  boxReset(nb);
-  for (int i = 0; i < n; i++) boxGrow(nb, loadBox(primBox + 6 * i));
-  Node8 nd;
-  nd.childBase = 0;
-  nd.primBase = 0;
-  nd.imask = 0;
-  Box6 slotBox[8];
-  for (int s = 0; s < 8; s++) wideMembers[s] = KF_MEMBER_EMPTY;
-  nd.triMask = ((1u << n) - 1u) * 0x00010001u;
-  nd.reserved = 0;
-  slotBox[0] = nb;
-  for (int i = 0; i < n; i++) outPrim[i] = uint32_t(i);
-  quantiseNode(nd, nb, slotBox, 1u);
-  outNodes[0] = nd;
-  storeBox(rootBox, nb);
 }
 
 // Top-level root for a single instance: node 0 with one child, the InstNode at index 1.
@@ -1075,73 +1013,6 @@ __global__ void k_requantise(const uint32_t* __restrict__ nWide, const int* __re
   Node8 nd = nodes[w];
   quantiseNode(nd, nb, slotBox, used);
   nodes[w] = nd;
-}
-
-// Bounding sphere of a geometry in object space: centre of its box, squared radius over all its
-// vertices (a float that is >= 0 orders like its bits, so atomicMax on the bits does the reduction).
-// It lives in the 80-byte record in front of the BLAS root (nodes[-1]) and is tested when a ray enters
-// the instance (kf_trace.cuh): the world box of a rotated or round object is far from tight, and every
-// needless entry costs a root node step or more.
-__global__ void k_blas_sphere(const KfrtVertex* __restrict__ verts, uint32_t nVerts, const int* __restrict__ sceneBox,
-                              float* __restrict__ header /* cx, cy, cz, r^2 (bits) */) {
-  const float cx = 0.5f * (orderedToFloat(sceneBox[0]) + orderedToFloat(sceneBox[3]));
-  const float cy = 0.5f * (orderedToFloat(sceneBox[1]) + orderedToFloat(sceneBox[4]));
-  const float cz = 0.5f * (orderedToFloat(sceneBox[2]) + orderedToFloat(sceneBox[5]));
-  float r2 = 0.0f;
-  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nVerts; v += gridDim.x * blockDim.x) {
-    const float dx = verts[v].pos[0] - cx, dy = verts[v].pos[1] - cy, dz = verts[v].pos[2] - cz;
-    r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(header) + 3, __float_as_uint(r2));
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    header[0] = cx;
-    header[1] = cy;
-    header[2] = cz;
-  }
-}
-
-// Shading records in primitive order (see ShadeTri): plain copies of the vertex attributes.
-__global__ void k_write_shade_tris(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
-                                   const uint32_t* __restrict__ matIndex, uint32_t n, ShadeTri* __restrict__ out) {
-  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
-  if (prim >= n) return;
-  const KfrtVertex& a = verts[idx[3 * prim + 0]];
-  const KfrtVertex& b = verts[idx[3 * prim + 1]];
-  const KfrtVertex& c = verts[idx[3 * prim + 2]];
-  ShadeTri t;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    t.n0[k] = a.normal[k];
-    t.n1[k] = b.normal[k];
-    t.n2[k] = c.normal[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    t.uv0[k] = a.texCoord[k];
-    t.uv1[k] = b.texCoord[k];
-    t.uv2[k] = c.texCoord[k];
-  }
-  t.matIndex = matIndex[prim];
-  out[prim] = t;
-}
-
-// Triangles in leaf order: v0, e1 = v1 - v0, e2 = v2 - v0 (single IEEE subtractions, like the oracle).
-__global__ void k_write_tris(const KfrtVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
-                             const uint32_t* __restrict__ order, uint32_t n, Tri48* __restrict__ out) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t prim = order[k];
-  const float* p0 = verts[idx[3 * prim + 0]].pos;
-  const float* p1 = verts[idx[3 * prim + 1]].pos;
-  const float* p2 = verts[idx[3 * prim + 2]].pos;
-  Tri48 t;
-  t.v0x = p0[0]; t.v0y = p0[1]; t.v0z = p0[2];
-  t.prim = prim;
-  t.e1x = csub(p1[0], p0[0]); t.e1y = csub(p1[1], p0[1]); t.e1z = csub(p1[2], p0[2]); t.pad1 = 0.0f;
-  t.e2x = csub(p2[0], p0[0]); t.e2y = csub(p2[1], p0[1]); t.e2z = csub(p2[2], p0[2]); t.pad2 = 0.0f;
-  out[k] = t;
 }
 
 }  // namespace kf

@@ -116,6 +116,22 @@ KF_HD uint32_t lcg(uint32_t& prev) {
   prev = 1664525u * prev + 1013904223u;
   return prev & 0x00FFFFFFu;
 }
+// The LCG state after n more steps, in O(log n): x -> a^n x + c (a^n - 1) / (a - 1) mod 2^32, by squaring
+// the affine map (the state after n calls of lcg(), bit for bit).
+KF_HD uint32_t lcgSkip(uint32_t state, uint32_t n) {
+  uint32_t mul = 1664525u, add = 1013904223u;  // the map of 2^k steps
+  uint32_t accMul = 1u, accAdd = 0u;           // the map of the steps taken so far
+  while (n) {
+    if (n & 1u) {
+      accMul *= mul;
+      accAdd = accAdd * mul + add;
+    }
+    add = (mul + 1u) * add;
+    mul *= mul;
+    n >>= 1;
+  }
+  return accMul * state + accAdd;
+}
 // float(lcg)/float(2^24): the 24-bit integer converts exactly and the division by a power of two is
 // exact, so a multiply by 2^-24 is bit-identical to the reference's division.
 KF_HD float rnd(uint32_t& prev) { return float(lcg(prev)) * (1.0f / 16777216.0f); }

@@ -7,10 +7,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include "kf_blas_batch.cuh"
 #include "kf_bvh_build.cuh"
 #include "kf_common.cuh"
 #include "kf_shade.cuh"
@@ -63,6 +65,17 @@ struct DevBuf {
   }
 };
 
+// Device storage shared by the bottom-level structures of one build batch (nodes, triangles and shading
+// records of all its geometries in one allocation); returned to the stream-ordered pool when the last
+// geometry that lives in it is rebuilt or freed.
+struct BlasBlock {
+  void* p = nullptr;
+  cudaStream_t stream = nullptr;
+  ~BlasBlock() {
+    if (p) cudaFreeAsync(p, stream);
+  }
+};
+
 struct GeomHost {
   bool present = false, dirty = false, opaque = true, hide = false;
   uint32_t nVerts = 0, nIdx = 0, nMat = 0;
@@ -70,14 +83,16 @@ struct GeomHost {
   uint32_t* idx = nullptr;
   uint32_t* matIndex = nullptr;
   Node8* nodes = nullptr;       // root; the record in front of it (nodesAlloc) holds the bounding sphere
-  Node8* nodesAlloc = nullptr;
+  Node8* nodesAlloc = nullptr;  // nodesAlloc, tris and shade point into `block`
   Tri48* tris = nullptr;
   ShadeTri* shade = nullptr;
+  std::shared_ptr<BlasBlock> block;
   uint32_t nNodes = 0;
   uint32_t depth = 0;  // levels of its wide tree
   float box[6] = {0, 0, 0, 0, 0, 0};
   void freeAll() {
-    cudaFree(verts); cudaFree(idx); cudaFree(matIndex); cudaFree(nodesAlloc); cudaFree(tris); cudaFree(shade);
+    cudaFree(verts); cudaFree(idx); cudaFree(matIndex);
+    block.reset();
     verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; nodesAlloc = nullptr; tris = nullptr; shade = nullptr;
     present = false;
     nNodes = 0;
@@ -102,17 +117,23 @@ struct BuildState {
   DevBuf<int> parent, wideBinary, wideMembers;
   DevBuf<float> nodeBox;
   DevBuf<Node8> outNodes;
+  // scratch of the batched bottom-level build (kf_blas_batch.cuh)
+  DevBuf<BatchGeom> batchGeoms;
+  DevBuf<uint32_t> primGeom, batchCounters;
+  DevBuf<int> batchBoxes;
   // scratch of the top-level SAH build (k_tlas_sah)
   DevBuf<uint32_t> sahSegOf, sahBinCount, sahPre, sahSegPre;
   DevBuf<int4> sahSegs, sahDecision;
   DevBuf<float2> sahDecisionF;
   DevBuf<int> sahBounds, sahBinBox;
   uint32_t* sortedVals = nullptr;  // valsA or valsB after the sort
+  uint64_t* sortedKeys = nullptr;  // keysA or keysB after the sort
   void release() {
     primBox.release(); sceneBox.release(); keysA.release(); keysB.release(); valsA.release();
     valsB.release(); hist.release(); flags.release(); outPrim.release(); counters.release();
     children.release(); range.release(); parent.release(); wideBinary.release();
     wideMembers.release(); nodeBox.release(); outNodes.release(); slotOfInst.release();
+    batchGeoms.release(); primGeom.release(); batchCounters.release(); batchBoxes.release();
     sahSegOf.release(); sahBinCount.release(); sahPre.release(); sahSegPre.release(); sahSegs.release();
     sahDecision.release(); sahDecisionF.release(); sahBounds.release(); sahBinBox.release();
   }
@@ -257,12 +278,14 @@ static inline unsigned gridFor(size_t n, unsigned block) { return unsigned((n + 
 // ------------------------------------------------------------------------------------------------
 // BVH build sequencing
 // ------------------------------------------------------------------------------------------------
-static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
+// keyBits: the keys have no bit set at or above it, so the passes over higher digits are skipped.
+static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n, int keyBits = 64) {
   const uint32_t numBlocks = gridFor(n, KF_SORT_TILE);
   KF_CUDA(ctx, st.hist.ensure(size_t(256) * numBlocks));
   uint64_t *kin = st.keysA.p, *kout = st.keysB.p;
   uint32_t *vin = st.valsA.p, *vout = st.valsB.p;
-  for (int pass = 0; pass < 8; pass++) {
+  const int passes = std::min(8, std::max(1, (keyBits + 7) / 8));
+  for (int pass = 0; pass < passes; pass++) {
     const int shift = pass * 8;
     k_sort_hist<<<numBlocks, KF_SORT_THREADS, 0, ctx->stream>>>(kin, n, shift, st.hist.p, numBlocks);
     k_sort_scan<<<1, 1024, 0, ctx->stream>>>(st.hist.p, 256u * numBlocks);
@@ -271,8 +294,9 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n) {
     std::swap(kin, kout);
     std::swap(vin, vout);
   }
-  // 8 passes: data is back in A
+  // an even number of passes leaves the data in A, an odd one in B
   st.sortedVals = vin;
+  st.sortedKeys = kin;
   KF_CUDA(ctx, cudaGetLastError());
   return KFRT_OK;
 }
@@ -345,86 +369,6 @@ static int reserveBuild(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas)
   return KFRT_OK;
 }
 
-static int buildWideBvh(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
-  st.n = n;
-  const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
-  {
-    int rc = reserveBuild(ctx, st, n, tlas);
-    if (rc) return rc;
-  }
-  // top level: the InstNode slots of the array are written later (k_instance_setup, into the copy the
-  // traversal reads); give them defined bytes until then
-  if (tlas) KF_CUDA(ctx, cudaMemsetAsync(st.outNodes.p, 0, sizeof(Node8) * maxNodes, ctx->stream));
-  if (tlas && n == 1) {
-    k_single_instance_root<<<1, 32, 0, ctx->stream>>>(st.primBox.p, st.outNodes.p, st.wideBinary.p,
-                                                      st.wideMembers.p, st.slotOfInst.p, st.nodeBox.p);
-    st.nWide = 2;
-    st.depth = 1;
-    KF_CUDA(ctx, cudaGetLastError());
-    return KFRT_OK;
-  }
-  if (!tlas && n <= KF_LEAF_MAX) {
-    k_single_leaf_root<<<1, 32, 0, ctx->stream>>>(int(n), st.primBox.p, st.outNodes.p, st.outPrim.p,
-                                                  st.wideMembers.p, st.nodeBox.p);
-    st.nWide = 1;
-    st.depth = 1;
-    KF_CUDA(ctx, cudaGetLastError());
-    return KFRT_OK;
-  }
-  if (tlas && n <= KF_TLAS_SAH_MAX) {
-    int rc = sahTopLevelHierarchy(ctx, st, n);
-    if (rc) return rc;
-  } else {
-    k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
-    int rc = radixSort(ctx, st, n);
-    if (rc) return rc;
-    k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
-                                                                   st.range.p, st.parent.p);
-  }
-  KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));
-  k_lbvh_bounds<<<gridFor(n, 256), 256, 0, ctx->stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p,
-                                                          st.sortedVals, st.nodeBox.p, st.flags.p);
-  // collapse, one launch per level of the wide tree; the level ranges stay on the device and the
-  // host looks at them once per batch of launches
-  const uint32_t init[5] = {1u, 0u, 0u, 1u, 0u};
-  const int zero = 0;
-  KF_CUDA(ctx, cudaMemcpyAsync(st.counters.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(st.wideBinary.p, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CollapseArgs a;
-  a.n = int(n);
-  a.children = st.children.p;
-  a.range = st.range.p;
-  a.nodeBox = st.nodeBox.p;
-  a.primBox = st.primBox.p;
-  a.vals = st.sortedVals;
-  a.outNodes = st.outNodes.p;
-  a.outPrim = st.outPrim.p;
-  a.wideBinary = st.wideBinary.p;
-  a.wideMembers = st.wideMembers.p;
-  a.counters = st.counters.p;
-  a.slotOfInst = tlas ? st.slotOfInst.p : nullptr;
-  const unsigned grid = std::min<unsigned>(gridFor(maxNodes, 64), unsigned(ctx->numSMs) * 16u);
-  uint32_t lv[5] = {0, 0, 0, 1, 0};
-  // a balanced 8-wide tree over n / 2 leaves has log8(n / 2) levels; LBVH trees are a little deeper
-  int levels = 4;
-  for (uint32_t m = n; m > 16; m >>= 3) levels++;
-  while (lv[2] < lv[3]) {
-    for (int level = 0; level < levels; level++) {
-      if (tlas) k_collapse_level<true><<<grid, 64, 0, ctx->stream>>>(a);
-      else k_collapse_level<false><<<grid, 64, 0, ctx->stream>>>(a);
-      k_next_level<<<1, 1, 0, ctx->stream>>>(st.counters.p);
-    }
-    KF_CUDA(ctx, cudaMemcpyAsync(lv, st.counters.p, sizeof(lv), cudaMemcpyDeviceToHost, ctx->stream));
-    KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (lv[0] > maxNodes) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
-  }
-  const uint32_t hi = lv[0];
-  st.depth = lv[4];
-  st.nWide = hi;
-  KF_CUDA(ctx, cudaGetLastError());
-  return KFRT_OK;
-}
-
 static void orderedBoxToFloat(const int* ib, float* out) {
   for (int k = 0; k < 6; k++) {
     int i = ib[k];
@@ -433,43 +377,152 @@ static void orderedBoxToFloat(const int* ib, float* out) {
   }
 }
 
-static int buildOneBlas(KfrtContext* ctx, GeomHost& g) {
-  // nodes / triangles come from the stream-ordered pool: no device-wide synchronisation per BLAS
-  if (g.nodesAlloc) cudaFreeAsync(g.nodesAlloc, ctx->stream);
-  if (g.tris) cudaFreeAsync(g.tris, ctx->stream);
-  if (g.shade) cudaFreeAsync(g.shade, ctx->stream);
-  g.nodes = nullptr;
-  g.nodesAlloc = nullptr;
-  g.tris = nullptr;
-  g.shade = nullptr;
-  g.nNodes = 0;
-  const uint32_t nTris = g.nIdx / 3;
-  if (nTris == 0 || g.hide) return KFRT_OK;
+// A batch holds at most KF_BATCH_MAX_GEOMS geometries (the geometry index takes the top 10 key bits) and,
+// unless a single geometry is larger, KF_BATCH_MAX_TRIS triangles (what bounds the build scratch: about
+// 0.25 KB per triangle).
+#define KF_BATCH_MAX_TRIS (size_t(4) << 20)
+
+// Builds the bottom-level structures of geoms[first, first + count) of `list` in one pass (see
+// kf_blas_batch.cuh).  One stream synchronisation per batch: node counts, depths and boxes come back
+// together before the final storage is sized.
+static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t count) {
   BuildState& st = ctx->blasBuild;
-  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * nTris));
-  KF_CUDA(ctx, st.sceneBox.ensure(6));
-  k_init_scene_box<<<1, 32, 0, ctx->stream>>>(st.sceneBox.p);
-  k_tri_boxes<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, nTris, st.primBox.p, st.sceneBox.p);
-  // the geometry's box travels with the synchronisation the collapse loop needs anyway
-  int ib[6];
-  KF_CUDA(ctx, cudaMemcpyAsync(ib, st.sceneBox.p, sizeof(ib), cudaMemcpyDeviceToHost, ctx->stream));
-  int rc = buildWideBvh(ctx, st, nTris, false);
-  if (rc) return rc;
-  if (nTris <= KF_LEAF_MAX) KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.nodesAlloc), sizeof(Node8) * (size_t(st.nWide) + 1), ctx->stream));
-  g.nodes = g.nodesAlloc + 1;
-  KF_CUDA(ctx, cudaMemsetAsync(g.nodesAlloc, 0, sizeof(Node8), ctx->stream));
-  k_blas_sphere<<<std::min<unsigned>(gridFor(g.nVerts, 256), unsigned(ctx->numSMs) * 4u), 256, 0, ctx->stream>>>(
-      g.verts, g.nVerts, st.sceneBox.p, reinterpret_cast<float*>(g.nodesAlloc));
-  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.tris), sizeof(Tri48) * nTris, ctx->stream));
-  KF_CUDA(ctx, cudaMemcpyAsync(g.nodes, st.outNodes.p, sizeof(Node8) * st.nWide, cudaMemcpyDeviceToDevice,
-                               ctx->stream));
-  k_write_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, st.outPrim.p, nTris, g.tris);
-  KF_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&g.shade), sizeof(ShadeTri) * nTris, ctx->stream));
-  k_write_shade_tris<<<gridFor(nTris, 256), 256, 0, ctx->stream>>>(g.verts, g.idx, g.matIndex, nTris, g.shade);
-  orderedBoxToFloat(ib, g.box);
-  g.nNodes = st.nWide;
-  g.depth = st.depth;
+  cudaStream_t stream = ctx->stream;
+  std::vector<BatchGeom> table(count);
+  uint32_t nTris = 0, nodeSlots = 0, maxTris = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    const GeomHost& g = *list[i];
+    BatchGeom& b = table[i];
+    b.verts = g.verts;
+    b.idx = g.idx;
+    b.matIndex = g.matIndex;
+    b.nVerts = g.nVerts;
+    b.nTris = g.nIdx / 3;
+    b.triOffset = nTris;
+    b.nodeOffset = nodeSlots;
+    b.nodesAlloc = nullptr;
+    b.tris = nullptr;
+    b.shade = nullptr;
+    nTris += b.nTris;
+    nodeSlots += b.nTris + 1;
+    maxTris = std::max(maxTris, b.nTris);
+  }
+  const uint32_t n = nTris;
+  KF_CUDA(ctx, st.batchGeoms.ensure(count));
+  KF_CUDA(ctx, st.batchCounters.ensure(size_t(KF_BATCH_COUNTERS) * count));
+  KF_CUDA(ctx, st.batchBoxes.ensure(size_t(6) * count));
+  KF_CUDA(ctx, st.primGeom.ensure(n));
+  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * n));
+  KF_CUDA(ctx, st.hist.ensure(size_t(256) * gridFor(n, KF_SORT_TILE)));
+  KF_CUDA(ctx, st.keysA.ensure(n));
+  KF_CUDA(ctx, st.keysB.ensure(n));
+  KF_CUDA(ctx, st.valsA.ensure(n));
+  KF_CUDA(ctx, st.valsB.ensure(n));
+  KF_CUDA(ctx, st.children.ensure(n));
+  KF_CUDA(ctx, st.range.ensure(n));
+  KF_CUDA(ctx, st.parent.ensure(size_t(2) * n));
+  KF_CUDA(ctx, st.flags.ensure(n));
+  KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * n));
+  KF_CUDA(ctx, st.outNodes.ensure(nodeSlots));
+  KF_CUDA(ctx, st.wideBinary.ensure(nodeSlots));
+  KF_CUDA(ctx, st.outPrim.ensure(n));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.batchGeoms.p, table.data(), sizeof(BatchGeom) * count, cudaMemcpyHostToDevice, stream));
+  k_batch_init<<<gridFor(6 * size_t(count), 256), 256, 0, stream>>>(st.batchBoxes.p, count);
+  k_batch_tri_boxes<<<gridFor(n, 256), 256, 0, stream>>>(st.batchGeoms.p, count, n, st.primBox.p, st.primGeom.p, st.batchBoxes.p);
+  if (n > 1) {
+    k_batch_morton<<<gridFor(n, 256), 256, 0, stream>>>(st.primBox.p, st.primGeom.p, n, st.batchBoxes.p, st.keysA.p, st.valsA.p);
+    int geomBits = 0;
+    while ((1u << geomBits) < count) geomBits++;
+    int rc = radixSort(ctx, st, n, 3 * KF_BATCH_MORTON_BITS + geomBits);
+    if (rc) return rc;
+    k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, stream>>>(st.sortedKeys, int(n), st.children.p, st.range.p, st.parent.p);
+    KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, stream));
+    k_lbvh_bounds<<<gridFor(n, 256), 256, 0, stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p, st.sortedVals,
+                                                       st.nodeBox.p, st.flags.p);
+  } else {
+    const uint32_t zero = 0;
+    KF_CUDA(ctx, cudaMemcpyAsync(st.valsA.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+    st.sortedVals = st.valsA.p;
+  }
+  k_batch_roots<<<gridFor(count, 128), 128, 0, stream>>>(st.batchGeoms.p, count, st.range.p, n, st.batchCounters.p, st.wideBinary.p);
+  BatchCollapseArgs ca;
+  ca.geoms = st.batchGeoms.p;
+  ca.nGeoms = count;
+  ca.base.n = int(n);
+  ca.base.children = st.children.p;
+  ca.base.range = st.range.p;
+  ca.base.nodeBox = st.nodeBox.p;
+  ca.base.primBox = st.primBox.p;
+  ca.base.vals = st.sortedVals;
+  ca.base.outNodes = st.outNodes.p;
+  ca.base.outPrim = st.outPrim.p;
+  ca.base.wideBinary = st.wideBinary.p;
+  ca.base.wideMembers = nullptr;
+  ca.base.counters = st.batchCounters.p;
+  ca.base.slotOfInst = nullptr;
+  // a level of the largest geometry has at most ~maxTris / 2 nodes; a few blocks per geometry stride over it
+  const unsigned bx = std::max(1u, std::min<unsigned>(gridFor(maxTris / 4 + 1, 64), std::max(1u, unsigned(ctx->numSMs) * 16u / count)));
+  std::vector<uint32_t> counters(size_t(KF_BATCH_COUNTERS) * count);
+  std::vector<int> boxes(size_t(6) * count);
+  // a balanced 8-wide tree over n / 2 leaves has log8(n / 2) levels; LBVH trees are a little deeper
+  int levels = 4;
+  for (uint32_t m = maxTris; m > 16; m >>= 3) levels++;
+  for (bool done = false; !done;) {
+    for (int level = 0; level < levels; level++) {
+      k_batch_collapse_level<<<dim3(bx, count), 64, 0, stream>>>(ca);
+      k_batch_next_level<<<gridFor(count, 128), 128, 0, stream>>>(st.batchCounters.p, count);
+    }
+    KF_CUDA(ctx, cudaMemcpyAsync(counters.data(), st.batchCounters.p, sizeof(uint32_t) * counters.size(), cudaMemcpyDeviceToHost, stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(boxes.data(), st.batchBoxes.p, sizeof(int) * boxes.size(), cudaMemcpyDeviceToHost, stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(stream));
+    done = true;
+    for (uint32_t i = 0; i < count; i++) {
+      const uint32_t* c = &counters[size_t(KF_BATCH_COUNTERS) * i];
+      if (c[0] > table[i].nTris + 1) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
+      if (c[2] < c[3]) done = false;
+    }
+    levels = 4;
+  }
+  // final storage: one allocation for the batch, 256-byte aligned pieces
+  auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+  size_t bytes = 0;
+  std::vector<size_t> offNodes(count), offTris(count), offShade(count);
+  for (uint32_t i = 0; i < count; i++) {
+    const uint32_t nWide = counters[size_t(KF_BATCH_COUNTERS) * i];
+    offNodes[i] = bytes; bytes = align(bytes + sizeof(Node8) * (size_t(nWide) + 1));
+    offTris[i] = bytes; bytes = align(bytes + sizeof(Tri48) * table[i].nTris);
+    offShade[i] = bytes; bytes = align(bytes + sizeof(ShadeTri) * table[i].nTris);
+  }
+  auto block = std::make_shared<BlasBlock>();
+  block->stream = stream;
+  KF_CUDA(ctx, cudaMallocAsync(&block->p, bytes, stream));
+  char* base = static_cast<char*>(block->p);
+  for (uint32_t i = 0; i < count; i++) {
+    GeomHost& g = *list[i];
+    g.block = block;
+    g.nodesAlloc = reinterpret_cast<Node8*>(base + offNodes[i]);
+    g.nodes = g.nodesAlloc + 1;
+    g.tris = reinterpret_cast<Tri48*>(base + offTris[i]);
+    g.shade = reinterpret_cast<ShadeTri*>(base + offShade[i]);
+    g.nNodes = counters[size_t(KF_BATCH_COUNTERS) * i];
+    g.depth = counters[size_t(KF_BATCH_COUNTERS) * i + 4];
+    orderedBoxToFloat(&boxes[size_t(6) * i], g.box);
+    table[i].nodesAlloc = g.nodesAlloc;
+    table[i].tris = g.tris;
+    table[i].shade = g.shade;
+    KF_CUDA(ctx, cudaMemsetAsync(g.nodesAlloc, 0, sizeof(Node8), stream));  // the header record
+  }
+  KF_CUDA(ctx, cudaMemcpyAsync(st.batchGeoms.p, table.data(), sizeof(BatchGeom) * count, cudaMemcpyHostToDevice, stream));
+  k_batch_copy_nodes<<<dim3(bx, count), 128, 0, stream>>>(st.batchGeoms.p, st.outNodes.p, st.batchCounters.p);
+  uint32_t maxVerts = 1;
+  for (uint32_t i = 0; i < count; i++) maxVerts = std::max(maxVerts, table[i].nVerts);
+  const unsigned sx = std::max(1u, std::min<unsigned>(gridFor(maxVerts, 1024), std::max(1u, unsigned(ctx->numSMs) * 8u / count)));
+  k_batch_spheres<<<dim3(sx, count), 256, 0, stream>>>(st.batchGeoms.p, st.batchBoxes.p);
+  k_batch_write_tris<<<gridFor(n, 256), 256, 0, stream>>>(st.batchGeoms.p, st.primGeom.p, st.outPrim.p, n);
+  k_batch_write_shade_tris<<<gridFor(n, 256), 256, 0, stream>>>(st.batchGeoms.p, st.primGeom.p, n);
+  KF_CUDA(ctx, cudaGetLastError());
+  // the table on the host goes out of scope: the copy above must have read it
+  KF_CUDA(ctx, cudaStreamSynchronize(stream));
   return KFRT_OK;
 }
 
@@ -861,19 +914,31 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
 
 int kfrtBuildBlas(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
-  // size the build scratch once, for the largest geometry of this batch
-  uint32_t maxTris = 0;
-  for (auto& g : ctx->geoms)
-    if (g.present && g.dirty && !g.hide) maxTris = std::max(maxTris, g.nIdx / 3);
-  if (maxTris > KF_LEAF_MAX) {
-    int rc = reserveBuild(ctx, ctx->blasBuild, maxTris, false);
-    if (rc) return rc;
-  }
+  // all geometries uploaded since the last build, in batches (kf_blas_batch.cuh)
+  std::vector<GeomHost*> todo;
   for (auto& g : ctx->geoms) {
     if (!g.present || !g.dirty) continue;
-    int rc = buildOneBlas(ctx, g);
-    if (rc) return rc;
+    g.block.reset();  // the old structure goes back to the pool behind the work already enqueued
+    g.nodes = nullptr;
+    g.nodesAlloc = nullptr;
+    g.tris = nullptr;
+    g.shade = nullptr;
+    g.nNodes = 0;
+    g.depth = 0;
     g.dirty = false;
+    if (g.nIdx / 3 == 0 || g.hide) continue;  // hidden geometries get no bottom level (reference rt.cpp:153-157)
+    todo.push_back(&g);
+  }
+  for (size_t first = 0; first < todo.size();) {
+    size_t last = first, tris = 0;
+    while (last < todo.size() && last - first < KF_BATCH_MAX_GEOMS &&
+           (last == first || tris + todo[last]->nIdx / 3 <= KF_BATCH_MAX_TRIS)) {
+      tris += todo[last]->nIdx / 3;
+      last++;
+    }
+    int rc = buildBlasBatch(ctx, todo.data() + first, uint32_t(last - first));
+    if (rc) return rc;
+    first = last;
   }
   KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->blasBuilt = true;
@@ -994,7 +1059,7 @@ static int buildTopLevel(KfrtContext* ctx, bool wait) {
       k_morton<<<gridFor(n, 256), 256, 0, ctx->stream>>>(st.primBox.p, n, st.sceneBox.p, st.keysA.p, st.valsA.p);
       rc = radixSort(ctx, st, n);
       if (rc) return rc;
-      k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.keysA.p, int(n), st.children.p,
+      k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, ctx->stream>>>(st.sortedKeys, int(n), st.children.p,
                                                                      st.range.p, st.parent.p);
     }
     KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, ctx->stream));

@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
       const uint32_t i = a.batchBegin + s;  // global sample index
       const uint32_t mapping = y * a.w + x;
       uint32_t seed = tea(mapping, a.clockBase);
-      // the pixel-jitter stream is shared by all samples of the pixel: skip the draws of samples < i
-      for (uint32_t k = 0; k < 2 * i; k++) lcg(seed);
+      // the pixel-jitter stream is shared by all samples of the pixel (rgen:30-37): skip the two draws of
+      // each of the samples < i, in O(log i) instead of 2 i dependent steps
+      seed = lcgSkip(seed, 2u * i);
       uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
       V3 o, d;
       cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);

@@ -21,6 +21,8 @@ struct Recipe {
 ///   "active"       config 4  eActive (Example.hpp:479-645) with an IR dot-pattern projector, stereo pair
 ///   "articulated"  config 5  2048 link instances (64 chains x 32 links), 64 cameras, animate() per frame
 ///   "million_obj"  config 3 with every mesh written to a Wavefront file and read back by loadScene()
+///   "spheres_ref"  config 1 with the reference's resources/models/suzanne.dae   } only where the reference tree
+///   "active_ref"   config 4 with suzanne.dae and resources/patterns/fakesense_j415.png } is mounted (KUAFU_REFERENCE)
 ///   "unique"       stress: config 3's layout with 204 un-instanced displaced blobs (1.0 M unique triangles)
 ///   "unique10m"    stress: 1 000 un-instanced blobs of 10 000 triangles (10.0 M unique triangles)
 ///   "file:<path>"  the meshes of an asset file (.obj / .dae / .stl / .gltf / .glb), framed by one camera

@@ -68,8 +68,18 @@ Camera* mainCamera(Kuafu& r, const Recipe& rc, int w, int h) {
   return cam;
 }
 
-// The objects shared by the eSpheres and eActive levels of the example app.
-void tableTop(Scene* scene, bool withGlassCube, float floorMetallic) {
+// Where the reference's own assets are, for the "_ref" recipes (they cannot ship with this repository).
+std::string referenceResource(const std::string& relative) {
+  const char* root = std::getenv("KUAFU_REFERENCE");
+  const std::string path = std::string(root && *root ? root : "/root/reference") + "/resources/" + relative;
+  std::ifstream probe(path, std::ios::binary);
+  if (!probe.good()) throw std::runtime_error("reference asset not found: " + path);
+  return path;
+}
+
+// The objects shared by the eSpheres and eActive levels of the example app.  refAssets: the scanned head
+// is the reference's resources/models/suzanne.dae (Example.hpp:292-306) instead of the stand-in.
+void tableTop(Scene* scene, bool withGlassCube, float floorMetallic, bool refAssets = false) {
   auto floor = createYZPlane(true, material(glm::vec3(0.8f), 0.5f, floorMetallic, 0.1f));
   std::shared_ptr<Geometry> glassCube;
   if (withGlassCube) glassCube = createCube(true, material({1.0F, 0.7F, 0.7F}, 0.0f, 0.1f, 0.01f, 1.45f, 1.0f));
@@ -99,7 +109,16 @@ void tableTop(Scene* scene, bool withGlassCube, float floorMetallic) {
   scene->setGeometryInstances(insts);
 
   // the scanned head model of the example (suzanne.dae) -> procedural stand-in of equal size
-  auto head = createBlob(material({0.2F, 0.2F, 0.2F}, 0.0f, 1.0f, 0.05f, 1.45f));
+  const NiceMaterial headMat = material({0.2F, 0.2F, 0.2F}, 0.0f, 1.0f, 0.05f, 1.45f);
+  std::shared_ptr<Geometry> head;
+  if (refAssets) {
+    auto meshes = loadScene(referenceResource("models/suzanne.dae"), true);
+    if (meshes.empty()) throw std::runtime_error("suzanne.dae holds no mesh");
+    head = meshes.front();
+    head->setMaterial(headMat);
+  } else {
+    head = createBlob(headMat);
+  }
   glm::mat4 t = glm::translate(glm::mat4(1.0F), {-2.0F, 5.0F, 2.F});
   t = glm::rotate(t, glm::radians(-90.f), {0, 0, 1});
   t = glm::rotate(t, glm::radians(-20.f), {1, 0, 0});
@@ -108,7 +127,7 @@ void tableTop(Scene* scene, bool withGlassCube, float floorMetallic) {
   scene->submitGeometryInstance(instance(head, t));
 }
 
-std::vector<Camera*> loadSpheres(Kuafu& r, const Recipe& rc) {  // config 1
+std::vector<Camera*> loadSpheres(Kuafu& r, const Recipe& rc, bool refAssets = false) {  // config 1
   applyConfig(r, rc, 4, 8, false);
   Scene* scene = r.getScene();
   Camera* cam = mainCamera(r, rc, 800, 600);
@@ -121,7 +140,7 @@ std::vector<Camera*> loadSpheres(Kuafu& r, const Recipe& rc) {  // config 1
   sun->strength = 8;
   sun->softness = 0.5;
   scene->setDirectionalLight(sun);
-  tableTop(scene, true, 0.0f);
+  tableTop(scene, true, 0.0f, refAssets);
   scene->removeEnvironmentMap();
   return {cam};
 }
@@ -146,7 +165,7 @@ std::string irPattern() {
   return global::registerMemoryTexture("ir-dot-pattern", n, n, px.data());
 }
 
-std::vector<Camera*> loadActive(Kuafu& r, const Recipe& rc) {  // config 4
+std::vector<Camera*> loadActive(Kuafu& r, const Recipe& rc, bool refAssets = false) {  // config 4
   applyConfig(r, rc, 32, 8, false);
   Scene* scene = r.getScene();
   scene->setClearColor({0.64F, 0.60F, 0.52F, 0.0F});
@@ -156,9 +175,11 @@ std::vector<Camera*> loadActive(Kuafu& r, const Recipe& rc) {  // config 4
   projector->color = {1., 1., 1.};
   projector->strength = 1000;
   projector->softness = 0;  // the example's softness 1 is flagged as incorrectly implemented
-  projector->texPath = irPattern();
+  // Example.hpp:496: resources/patterns/fakesense_j415.png (3000 x 3000, 36 MB as RGBA8); the dot grid of
+  // irPattern() stands in for it where the reference tree is not mounted
+  projector->texPath = refAssets ? referenceResource("patterns/fakesense_j415.png") : irPattern();
   scene->addActiveLight(projector);
-  tableTop(scene, false, 0.9f);
+  tableTop(scene, false, 0.9f, refAssets);
   scene->removeEnvironmentMap();
   // stereo IR pair, 55 mm baseline along camera-right
   const int w = rc.width > 0 ? rc.width : 1280, h = rc.height > 0 ? rc.height : 720;
@@ -587,6 +608,8 @@ std::vector<Camera*> load(Kuafu& renderer, const Recipe& rc) {
   if (rc.name == "cornell") return loadCornell(renderer, rc);
   if (rc.name == "million") return loadMillion(renderer, rc);
   if (rc.name == "active") return loadActive(renderer, rc);
+  if (rc.name == "spheres_ref") return loadSpheres(renderer, rc, true);
+  if (rc.name == "active_ref") return loadActive(renderer, rc, true);
   if (rc.name == "articulated") return loadArticulated(renderer, rc);
   if (rc.name == "unique") return loadUnique(renderer, rc, 204, 50, 50);
   if (rc.name == "unique10m") return loadUnique(renderer, rc, 1000, 100, 51);

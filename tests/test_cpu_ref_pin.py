@@ -137,6 +137,27 @@ def test_shaders_vs_oracle_baseline_configs(built, name, w, h, spp, scale, clock
     assert_identical(a, b)
 
 
+REF_ASSET_CONFIGS = [("spheres_ref", 80, 60, 2, 0, 5), ("active_ref", 96, 54, 2, 0, 4)]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,w,h,spp,scale,clock", REF_ASSET_CONFIGS)
+def test_shaders_vs_oracle_with_the_reference_assets(built, name, w, h, spp, scale, clock):
+    """Configs 1 and 4 with the reference's own assets instead of the procedural stand-ins:
+    resources/models/suzanne.dae through the COLLADA importer and, for config 4, the projector pattern
+    resources/patterns/fakesense_j415.png (3000 x 3000) through the PNG reader (Example.hpp:292-306, 496).
+    The assets cannot ship, so these recipes exist only where /root/reference is mounted."""
+    if not os.path.exists("/root/reference/resources/patterns/fakesense_j415.png"):
+        pytest.skip("reference assets are not mounted")
+    sc = _config_scene(name, w, h, spp, scale)
+    assert sc.n_tris() > 270000  # the scanned head is in the scene
+    if name == "active_ref":
+        assert any(t.shape[:2] == (3000, 3000) for t in sc.textures)
+    a, b = both(sc, clock=clock)
+    assert_identical(a, b)
+    assert a["counters"]["shadowRays"] > 0
+
+
 @pytest.mark.parametrize("name,w,h,spp,scale,clock", CONFIGS)
 def test_oracle_vs_frozen_shader_outputs(built, name, w, h, spp, scale, clock):
     """tests/golden/ref_<name>.npz was written by the shim (make_golden.py --ref); no reference needed."""

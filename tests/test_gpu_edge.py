@@ -126,6 +126,53 @@ def test_many_overlapping_instances(rt, orc_mod):
     ctx.close()
 
 
+def test_batched_blas_build_edge_cases(rt, orc_mod):
+    """kfrtBuildBlas builds all uploaded geometries in one pass (kf_blas_batch.cuh): geometries of one, two
+    and three triangles next to tessellated spheres, a hidden one in the middle of the batch, more than
+    1024 geometries (two batches: the geometry index takes 10 key bits), and a rebuild of a single
+    re-uploaded geometry beside structures that stay -- all against the oracle, hit for hit."""
+    sc = pyscene.small_scene(seed=11, w=96, h=72, spp=1, depth=3, lights="dir", n_spheres=4, glass=False)
+    qv, qi = pyscene.quad()
+    mat = sc.mats[1]
+    one = sc.add_geometry(qv, qi[:3].copy(), mat)
+    two = sc.add_geometry(qv, qi.copy(), mat)
+    three = sc.add_geometry(qv, np.concatenate([qi, qi[:3][::-1]]).astype(np.uint32), mat)
+    hidden = sc.add_geometry(qv, qi.copy(), mat, hide=True)
+    for k, g in enumerate((one, two, three, hidden)):
+        sc.insts.append(pyscene.instance(pyscene.translate([-2.0 + 1.5 * k, -3.0, 0.5]) @ pyscene.rotate(0.6, [0, 1, 0]), g))
+    rng = np.random.default_rng(3)
+    first_tile = len(sc.geoms)
+    for k in range(1100):  # tiles of two triangles, each its own geometry
+        g = sc.add_geometry(qv, qi.copy(), mat)
+        pos = [rng.uniform(-6, 6), rng.uniform(-5, 5), rng.uniform(-0.5, 3.0)]
+        sc.insts.append(pyscene.instance(pyscene.translate(pos) @ pyscene.rotate(rng.uniform(0, 3), rng.normal(size=3)) @ pyscene.scale(0.25), g))
+    ctx, orc = rt.Context(0), orc_mod.Oracle()
+    ctx.set_limits(2048, 8192, 16, 4096)
+    sc.upload(ctx)
+    sc.upload(orc)
+    st = ctx.bvh_stats()
+    assert int(st["blasCount"]) == len(sc.geoms) and int(st["instanceCount"]) == len(sc.insts)
+    got, ref = parity.render_both(sc, ctx, orc)
+    parity.assert_hits_bit_exact(got, ref)
+    seen = set(np.unique(got["hit_ids"][..., 0]).tolist())
+    hidden_inst = [k for k, inst in enumerate(sc.insts) if int(inst["geometryIndex"]) == hidden]
+    assert not seen.intersection(hidden_inst)
+    assert len([k for k in seen if k >= 0 and int(sc.insts[k]["geometryIndex"]) >= first_tile]) > 50
+    # one geometry uploaded again with other triangles: only it is rebuilt, the rest keep their storage
+    sv, si = pyscene.uv_sphere(7, 9)
+    v, i, mi, op, hide = sc.geoms[two]
+    sc.geoms[two] = (sv, si, np.full(si.size, mi[0], np.uint32), op, hide)
+    ctx.upload_geometry(two, sv, si, sc.geoms[two][2], op, hide)
+    ctx.build_blas()
+    ctx.set_instances(np.array(sc.insts, wire.INSTANCE))
+    ctx.build_tlas()
+    orc2 = orc_mod.Oracle()
+    sc.upload(orc2)
+    got, ref = parity.render_both(sc, ctx, orc2)
+    parity.assert_hits_bit_exact(got, ref)
+    ctx.close()
+
+
 # ---- properties at the BASELINE frame size (config 3 through the facade; no oracle pass needed) ----
 @pytest.fixture(scope="module")
 def million(built):

@@ -119,3 +119,23 @@ def test_direct_abi_misuse_is_refused(mods):
     ctx.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, 1, 0)
     assert (ctx.download_aux(wire.AUX_HIT_IDS) == -1).all()
     ctx.close()
+
+
+@pytest.mark.parametrize("name,w,h,limit", [("million", 960, 540, 4.6), ("articulated", 512, 512, 6.6)])
+def test_device_top_level_build_quality(mods, name, w, h, limit):
+    """The top level is built on the device (k_tlas_sah, binned SAH in one launch).  Its quality shows in
+    the number of top-level node visits per ray: round 1's host-side SAH gave 4.39 on config 3 and 6.26 on
+    config 5 (profiles/r1_config_table.txt); the Morton-order hierarchy it replaced 5.70 and 9.10."""
+    host, rt, oracle = mods
+    r = host.Renderer(device=0, accumulate=False)
+    r.load_scene(name, w, h, 2)
+    ctx = rt.Context(handle=r.device_context())
+    r.run()
+    ctx.set_detail_counters(True)
+    r.run()
+    c = ctx.counters()
+    ctx.set_detail_counters(False)
+    rays = int(c["extensionRays"]) + int(c["shadowRays"])
+    per_ray = int(c["tlasNodeVisits"]) / rays
+    assert 1.0 < per_ray < limit, per_ray
+    r.close()
