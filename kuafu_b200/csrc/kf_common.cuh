@@ -137,6 +137,34 @@ KF_HD uint32_t lcgSkip(uint32_t state, uint32_t n) {
 KF_HD float rnd(uint32_t& prev) { return float(lcg(prev)) * (1.0f / 16777216.0f); }
 
 // ---------------------------------------------------------------------------------------------
+// Pieces shared by the stage kernels of the wavefront scheduler
+// ---------------------------------------------------------------------------------------------
+// Warp-aggregated append: one atomic per warp, lanes get consecutive positions.
+KF_D void queueAppend(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, bool pred, uint32_t value) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+// Russian roulette and hand-over to the next bounce (reference PathTrace.rgen:119-138).
+// Returns true when the path continues.
+KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, uint32_t& seed) {
+  if (allEq(weight, mk3(0.0f))) return false;
+  if (pc.russianRoulette && depth >= pc.russianRouletteMinBounces) {
+    const float p = fmaxf(weight.x, fmaxf(weight.y, weight.z));
+    const float r = rnd(seed);
+    if (r > p) return false;
+    weight *= 1.0f / p;
+  }
+  return depth < pc.maxPathDepth;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Acceleration-structure records
 // ---------------------------------------------------------------------------------------------
 // 8-wide compressed node, 80 bytes = 5 x 16 B loads.  Child boxes are 8-bit offsets from `p` on a

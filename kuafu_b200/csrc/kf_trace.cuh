@@ -42,6 +42,8 @@ struct TraceArgs {
   const float4* rayO;        // origin.xyz per slot
   const float4* rayD;        // direction.xyz (+ tmax in .w for occlusion rays) per slot
   const float4* seedSrc;     // stateW: .w = ray seed bits (closest hit, non-opaque geometry only)
+  // results are written in QUEUE order (entry i of the queue -> hitA[i], hitB[i]), so that the stage that
+  // consumes them reads them as a stream next to the queue itself instead of gathering them by slot
   float4* hitA;              // closest hit: t, u, v, prim bits
   int* hitB;                 // closest hit: inst | front << 31, -1 on miss; occlusion: 1 occluded / 0
   uint32_t* clear0;          // counters this stage resets for later stages (may be null)
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   uint2 stack[KF_STACK];
   int sp = 0;
   bool active = false, exhausted = false;
-  uint32_t slot = 0;
+  uint32_t qpos = 0;  // queue position of the lane's ray
   RaySetup r = setupRay(mk3(0.0f), mk3(1.0f));
   // The world-space ray setup waits in shared memory (written once, when the ray is fetched) while
   // the lane is inside a bottom-level structure (r then holds the object-space ray): ten registers
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
         if (!active) {
           const uint32_t qi = base + uint32_t(__popc(idle & laneLt));
           if (qi < count) {
-            slot = a.queue[qi];
+            qpos = qi;
+            const uint32_t slot = a.queue[qi];
             const float4 o4 = a.rayO[slot], d4 = a.rayD[slot];
             const V3 o = mk3(o4.x, o4.y, o4.z);
             const V3 d = mk3(d4.x, d4.y, d4.z);
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
         const uint32_t g = sc.instSsbo[curInst].geometryIndex;
         const uint32_t mi = __ldg(sc.geoms[g].matIndex + prim);
         const float alpha = sc.mats[mi].alpha;
-        const uint32_t seed = __float_as_uint(a.seedSrc[slot].w);
+        const uint32_t seed = __float_as_uint(a.seedSrc[a.queue[qpos]].w);
         if (alpha == 0.0f || anyHitRnd(seed, uint32_t(curInst), uint32_t(prim)) > alpha) ok = false;
       }
       if (ok) {
@@ -313,10 +316,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
 
     if (finished) {
       if (ANY) {
-        a.hitB[slot] = hit.inst >= 0 ? 1 : 0;
+        a.hitB[qpos] = hit.inst >= 0 ? 1 : 0;
       } else {
-        a.hitA[slot] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.prim));
-        a.hitB[slot] = hit.inst < 0 ? -1 : int(uint32_t(hit.inst) | (hit.front << 31));
+        a.hitA[qpos] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.prim));
+        a.hitB[qpos] = hit.inst < 0 ? -1 : int(uint32_t(hit.inst) | (hit.front << 31));
       }
       active = false;
     }

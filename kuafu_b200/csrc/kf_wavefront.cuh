@@ -37,8 +37,8 @@ namespace kf {
 struct WfBuffers {
   float4* rayO;     // origin.xyz, -
   float4* rayD;     // direction.xyz, -
-  float4* hitA;     // t, u, v, prim (bits)
-  int* hitB;        // inst | front << 31, -1 on miss
+  float4* hitA;     // t, u, v, prim (bits)           } indexed by QUEUE position of the traversal stage that
+  int* hitB;        // inst | front << 31, -1 on miss } wrote them (kf_trace.cuh), not by slot
   float4* stateW;   // throughput weight.xyz, seed (bits)
   float4* stateC;   // colour.xyz, -
   float4* shadowL;  // L.xyz, maxDist
@@ -77,18 +77,6 @@ KF_D void slotToPixel(const WfArgs& a, uint32_t pixelSlot, uint32_t& cam, uint32
   const uint32_t ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
   x = tx * 8 + (lane & 7u);
   y = ty * 4 + (lane >> 3);
-}
-
-// Warp-aggregated append: one atomic per warp, lanes get consecutive positions.
-KF_D void queueAppend(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, bool pred, uint32_t value) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-  if (mask == 0u) return;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(mask) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
 KF_D void countAdd(unsigned long long* c, bool pred) {
@@ -133,19 +121,6 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
   }
 }
 
-// Russian roulette and hand-over to the next bounce (reference PathTrace.rgen:119-138).
-// Returns true when the path continues.
-KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, uint32_t& seed) {
-  if (allEq(weight, mk3(0.0f))) return false;
-  if (pc.russianRoulette && depth >= pc.russianRouletteMinBounces) {
-    const float p = fmaxf(weight.x, fmaxf(weight.y, weight.z));
-    const float r = rnd(seed);
-    if (r > p) return false;
-    weight *= 1.0f / p;
-  }
-  return depth < pc.maxPathDepth;
-}
-
 KF_D void storeCtx(float4* __restrict__ c, const Surface& sf, int k, V3 acc) {
   c[0] = make_float4(sf.N.x, sf.N.y, sf.N.z, sf.f);
   c[1] = make_float4(sf.V.x, sf.V.y, sf.V.z, sf.a2);
@@ -186,25 +161,27 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
   // (two copies of the staging arrays, used in turn: a warp still reading round n is separated from
   // the writers of round n + 2 by the two barriers of round n + 1)
   __shared__ uint32_t sSlotBuf[2][128];
+  __shared__ uint32_t sQposBuf[2][128];
   __shared__ int sHitBuf[2][128];
   __shared__ uint32_t sClassBuf[2][2][4];  // per warp: hits, misses
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t round = 0;
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride, round ^= 1u) {
     uint32_t* sSlot = sSlotBuf[round];
+    uint32_t* sQpos = sQposBuf[round];
     int* sHitB = sHitBuf[round];
     uint32_t(*sClass)[4] = sClassBuf[round];
     bool valid;
-    uint32_t slot = 0;
+    uint32_t slot = 0, qpos = 0;
     int hB = -1;
     {
       const uint32_t i = base + threadIdx.x;
       const bool have = i < count;
       uint32_t mySlot = 0;
       int myHit = -1;
-      if (have) {
+      if (have) {  // two independent streams: the queue entry and the hit record written at its position
         mySlot = queue[i];
-        myHit = a.b.hitB[mySlot];
+        myHit = a.b.hitB[i];
       }
       const uint32_t hitMask = __ballot_sync(0xffffffffu, have && myHit != -1);
       const uint32_t missMask = __ballot_sync(0xffffffffu, have && myHit == -1);
@@ -226,18 +203,20 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
         const uint32_t pos = myHit != -1 ? hitsBefore + __popc(hitMask & below)
                                          : hitsTotal + missesBefore + __popc(missMask & below);
         sSlot[pos] = mySlot;
+        sQpos[pos] = i;
         sHitB[pos] = myHit;
       }
       __syncthreads();
       valid = threadIdx.x < hitsTotal + missesTotal;
       if (valid) {
         slot = sSlot[threadIdx.x];
+        qpos = sQpos[threadIdx.x];
         hB = sHitB[threadIdx.x];
       }
     }
     bool toNext = false, toShadow = false, isHit = false;
     if (valid) {
-      const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[slot];
+      const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[qpos];
       const float4 sw = a.b.stateW[slot];
       float4 sc4 = a.b.stateC[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
@@ -345,7 +324,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
     uint32_t slot = 0;
     if (valid) {
       slot = queue[i];
-      const bool occluded = a.b.hitB[slot] != 0;  // written by k_wf_trace<true>
+      const bool occluded = a.b.hitB[i] != 0;  // written by k_wf_trace<true> at the queue position
       const float4 sw = a.b.stateW[slot], sc4 = a.b.stateC[slot], spec = a.b.shadowC[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
       uint32_t seed = __float_as_uint(sw.w);
