@@ -747,7 +747,7 @@ KF_D uint32_t exponentFor(float extent) {
   const float v = extent * (1.0f / 255.0f);
   int e = int((__float_as_uint(v) >> 23) & 0xffu) + 1;  // 2^(e-127) > v for normal v
   if (!(v > 0.0f)) e = 1;
-  return uint32_t(min(max(e, 1), 254));
+  return uint32_t(min(max(e, 1), 239));  // + 15 still fits the byte (KF_EXP_BIASED)
 }
 
 // Quantises the member boxes of one wide node.  slotBox[s] is ignored where slotUsed bit s is 0.
@@ -768,9 +768,9 @@ KF_D void quantiseNode(Node8& nd, const Box6& nbIn, const Box6* slotBox, uint32_
   const uint32_t ex = exponentFor(nb.hi[0] - nb.lo[0]);
   const uint32_t ey = exponentFor(nb.hi[1] - nb.lo[1]);
   const uint32_t ez = exponentFor(nb.hi[2] - nb.lo[2]);
-  nd.ex = uint8_t(ex);
-  nd.ey = uint8_t(ey);
-  nd.ez = uint8_t(ez);
+  nd.ex = uint8_t(ex + 15u);  // stored with the 2^15 of planeFloat() folded in (kf_traverse.cuh)
+  nd.ey = uint8_t(ey + 15u);
+  nd.ez = uint8_t(ez + 15u);
   const float isx = 1.0f / __uint_as_float(ex << 23);
   const float isy = 1.0f / __uint_as_float(ey << 23);
   const float isz = 1.0f / __uint_as_float(ez << 23);

@@ -168,11 +168,11 @@ KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, u
 // Acceleration-structure records
 // ---------------------------------------------------------------------------------------------
 // 8-wide compressed node, 80 bytes = 5 x 16 B loads.  Child boxes are 8-bit offsets from `p` on a
-// per-axis power-of-two grid 2^(e-127); children sit in octant-ordered slots so that traversal
+// per-axis power-of-two grid 2^(e-127) (stored: e + 15); children sit in octant-ordered slots so that traversal
 // order is a bit trick instead of a sort (after Ylitie, Karras, Laine 2017).
 struct __align__(16) Node8 {
   float px, py, pz;
-  uint8_t ex, ey, ez, imask;  // imask bit i: child slot i is an internal node
+  uint8_t ex, ey, ez, imask;  // biased grid exponents + 15 (see intersectNodeWords); imask bit i: child slot i is an internal node
   uint32_t childBase;         // index of first internal child (children are consecutive by slot)
   uint32_t primBase;          // index of first leaf primitive (triangle / instance-list entry)
   // Leaf children: slot s owns the two-bit field 2s..2s+1 of a 16-bit triangle mask (unary count of

@@ -95,10 +95,11 @@ KF_D uint32_t intersectNodeWords(const uint4 n0, const uint4 n1, const uint4 n2,
   primBase = n1.y;
   triMask = n1.z;
   imask = n0.w >> 24;
-  // per-axis grid step 2^(e-127), pre-multiplied by 2^15 (see planeFloat)
-  const float sx = __uint_as_float(((n0.w & 0xffu) + 15u) << 23);
-  const float sy = __uint_as_float((((n0.w >> 8) & 0xffu) + 15u) << 23);
-  const float sz = __uint_as_float((((n0.w >> 16) & 0xffu) + 15u) << 23);
+  // per-axis grid step 2^(e-127) times the 2^15 of planeFloat(): the builder stores e + 15, so a shift
+  // and a mask per axis put it in the exponent field
+  const float sx = __uint_as_float((n0.w << 23) & 0x7f800000u);
+  const float sy = __uint_as_float((n0.w << 15) & 0x7f800000u);
+  const float sz = __uint_as_float((n0.w << 7) & 0x7f800000u);
   const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
   const float bx = (__uint_as_float(n0.x) - r.ox) * r.ix - ax;
   const float by = (__uint_as_float(n0.y) - r.oy) * r.iy - ay;
@@ -107,35 +108,31 @@ KF_D uint32_t intersectNodeWords(const uint4 n0, const uint4 n1, const uint4 n2,
   const bool nx = r.ix < 0.0f, ny = r.iy < 0.0f, nz = r.iz < 0.0f;
   const uint32_t lox[2] = {n2.x, n2.y}, loy[2] = {n2.z, n2.w}, loz[2] = {n3.x, n3.y};
   const uint32_t hix[2] = {n3.z, n3.w}, hiy[2] = {n4.x, n4.y}, hiz[2] = {n4.z, n4.w};
+  // children 7 .. 0, so that the funnel shift below leaves the verdict of child s at bit s
   uint32_t miss = 0;
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
+  for (int h = 1; h >= 0; h--) {
     const uint32_t nearx = nx ? hix[h] : lox[h], farx = nx ? lox[h] : hix[h];
     const uint32_t neary = ny ? hiy[h] : loy[h], fary = ny ? loy[h] : hiy[h];
     const uint32_t nearz = nz ? hiz[h] : loz[h], farz = nz ? loz[h] : hiz[h];
-    uint32_t sgn[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 3; j >= 0; j--) {
       const float t0x = fmaf(planeFloat(nearx, j), ax, bx);
       const float t0y = fmaf(planeFloat(neary, j), ay, by);
       const float t0z = fmaf(planeFloat(nearz, j), az, bz);
       const float t1x = fmaf(planeFloat(farx, j), ax, bx);
       const float t1y = fmaf(planeFloat(fary, j), ay, by);
       const float t1z = fmaf(planeFloat(farz, j), az, bz);
-      const float t0 = fmaxf(fmaxf(t0x, t0y), t0z);
-      const float t1 = fminf(fminf(t1x, t1y), t1z);
-      // max(t0, tmin) <= min(t1, tmax)  <=>  none of these three differences is negative.  The
-      // subtractions run on the FMA pipe and the verdict is a sign bit (t1 is never NaN and a
-      // difference of equal values is +0; inf - inf gives the positive default NaN: a spurious hit,
-      // never a lost one).
-      sgn[j] = __float_as_uint(t1 - t0) | __float_as_uint(t1 - tmin) | __float_as_uint(tmax - t0);
+      // max(t0, tmin) <= min(t1, tmax): a three-input and a two-input min / max per side, then the sign of
+      // one subtraction (+0 on equality, never NaN: all operands are finite) shifted into the mask --
+      // 5 instructions per child where three sign-bit subtractions + OR + byte packing took 7 (measured on
+      // config 3: -3.3 % on both traversal stages).
+      const float t0 = fmaxf(fmaxf(fmaxf(t0x, t0y), t0z), tmin);
+      const float t1 = fminf(fminf(fminf(t1x, t1y), t1z), tmax);
+      miss = __funnelshift_l(__float_as_uint(t1 - t0), miss, 1);  // miss = miss << 1 | sign
     }
-    // sign bytes of the four children -> one nibble
-    const uint32_t x = __byte_perm(sgn[0], sgn[1], 0x7373u), y = __byte_perm(sgn[2], sgn[3], 0x7373u);
-    const uint32_t z = __byte_perm(x, y, 0x5410u) & 0x80808080u;
-    miss |= ((z * 0x00204081u) >> 28) << (4 * h);
   }
-  return miss;
+  return miss & 0xffu;
 }
 
 // The same test with the node fetched here (5 x 16 B loads).
