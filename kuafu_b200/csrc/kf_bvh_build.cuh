@@ -468,47 +468,49 @@ struct TlasSahArgs {
   int* cbounds;         // [bin slots][6] centroid bounds, ordered ints
   uint32_t* binCount;   // [bin slots][3][BINS]
   int* binBox;          // [bin slots][3][BINS][6] ordered ints
+  unsigned long long* bestKey;  // [bin slots] cheapest plane so far: cost bits << 32 | axis << 8 | bin
   int4* decision;       // [segments]: axis (-1: middle), split bin, nLeft, index of the first new segment
   float2* decisionF;    // [segments]: centroid lower bound on the axis, bins / extent
   uint32_t* pre;        // [n + 1] prefix sums over positions
-  uint32_t* segPre;     // [2][n / 2 + 2] prefix sums over segments: new segments, new bin slots
+  uint32_t* segPre;     // [n / 2 + 2] prefix sums over segments: new segments | new bin slots << 16
 };
 
 // Exclusive prefix sum of value(i), i in [0, total), into out[0..total] (out[total] = sum), by the
-// whole block.  `sh` holds 33 words.
+// whole block: every thread sums a contiguous run of ceil(total / threads) elements, one scan of the
+// thread totals (two barriers) gives each run its base, and the run is walked again to write the
+// prefixes.  (The first version scanned blockDim.x elements per round with four barriers a round; with
+// three scans per level the barriers were most of the top-level build.)  `sh` holds 33 words.
 template <class F>
 KF_D void blockExclusiveScan(uint32_t total, uint32_t* __restrict__ out, uint32_t* sh, F value) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-  if (threadIdx.x == 0) sh[32] = 0;
+  const uint32_t per = (total + blockDim.x - 1) / blockDim.x;
+  const uint32_t begin = min(total, threadIdx.x * per), end = min(total, begin + per);
+  uint32_t mine = 0;
+  for (uint32_t i = begin; i < end; i++) mine += value(i);
+  uint32_t x = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) sh[warp] = x;
   __syncthreads();
-  for (uint32_t base = 0; base < total; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < total ? value(i) : 0u;
-    uint32_t x = v;
+  if (warp == 0) {
+    uint32_t w = lane < nWarps ? sh[lane] : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
     }
-    if (lane == 31) sh[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = lane < nWarps ? sh[lane] : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += y;
-      }
-      sh[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t prefix = sh[32] + (warp > 0 ? sh[warp - 1] : 0u) + x - v;
-    if (i < total) out[i] = prefix;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) sh[32] = prefix + v;
-    __syncthreads();
+    sh[lane] = w;
   }
-  if (threadIdx.x == 0) out[total] = sh[32];
+  __syncthreads();
+  uint32_t running = (warp > 0 ? sh[warp - 1] : 0u) + x - mine;
+  for (uint32_t i = begin; i < end; i++) {
+    out[i] = running;
+    running += value(i);
+  }
+  if (threadIdx.x == blockDim.x - 1) out[total] = sh[nWarps - 1];
   __syncthreads();
 }
 
@@ -542,7 +544,6 @@ __global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs
     sCount[1] = 1;
     sCount[2] = n > 2 ? 1 : 0;
   }
-  uint32_t* segPreBig = a.segPre + maxSeg + 1;
   __syncthreads();
   for (;;) {
     const uint32_t nSeg = sCount[0], nBig = sCount[2];
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs
     // ---- centroid bounds and bins of every segment with more than two primitives --------------
     for (uint32_t i = tid; i < nBig * 6; i += T) a.cbounds[i] = floatToOrdered((i % 6) < 3 ? 3.0e38f : -3.0e38f);
     for (uint32_t i = tid; i < nBig * 3 * KF_TLAS_BINS; i += T) a.binCount[i] = 0;
+    for (uint32_t i = tid; i < nBig; i += T) a.bestKey[i] = ~0ull;
     for (uint32_t i = tid; i < nBig * 3 * KF_TLAS_BINS * 6; i += T)
       a.binBox[i] = floatToOrdered((i % 6) < 3 ? 3.0e38f : -3.0e38f);
     __syncthreads();
@@ -589,48 +591,82 @@ __global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs
       }
     }
     __syncthreads();
-    // ---- one thread per segment: sweep the bins, keep the cheapest plane -------------------------
+    // ---- sweep: sixteen lanes per (segment, axis), one bin each.  Suffix and prefix unions of the bin
+    // boxes by shuffles, the cost of the plane after every bin, the cheapest of the sixteen by a shuffle
+    // reduction, and the cheapest of the three axes by an atomic minimum on (cost, axis, bin) -- a lower
+    // axis or bin wins a tie, as in a serial sweep in that order.  (One thread per segment walking
+    // 3 x 2 x 16 bins of 7 words was the slowest phase of the build: 600 dependent loads per level.)
+    for (uint32_t item = tid >> 4; item < ((nBig * 3u + (T >> 4) - 1u) / (T >> 4)) * (T >> 4); item += T >> 4) {
+      const uint32_t lane16 = tid & 15u;
+      const bool live = item < nBig * 3u;
+      const uint32_t slot = live ? item / 3u : 0u, k = live ? item % 3u : 0u;
+      const float clo = orderedToFloat(a.cbounds[6 * slot + k]), chi = orderedToFloat(a.cbounds[6 * slot + 3 + k]);
+      const bool axisOk = live && csub(chi, clo) > 0.0f;
+      const size_t bi = (size_t(slot) * 3 + k) * KF_TLAS_BINS + lane16;
+      uint32_t cnt = axisOk ? a.binCount[bi] : 0u;
+      float lo[3], hi[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        lo[q] = axisOk ? orderedToFloat(a.binBox[6 * bi + q]) : 3.0e38f;
+        hi[q] = axisOk ? orderedToFloat(a.binBox[6 * bi + 3 + q]) : -3.0e38f;
+      }
+      // inclusive prefix (bins 0 .. b) and suffix (bins b .. 15) of count and box
+      uint32_t pc = cnt, sc = cnt;
+      float plo[3] = {lo[0], lo[1], lo[2]}, phi[3] = {hi[0], hi[1], hi[2]};
+      float slo[3] = {lo[0], lo[1], lo[2]}, shi[3] = {hi[0], hi[1], hi[2]};
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const uint32_t pcn = __shfl_up_sync(0xffffffffu, pc, o, 16), scn = __shfl_down_sync(0xffffffffu, sc, o, 16);
+        float pl[3], ph[3], sl[3], sh2[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          pl[q] = __shfl_up_sync(0xffffffffu, plo[q], o, 16);
+          ph[q] = __shfl_up_sync(0xffffffffu, phi[q], o, 16);
+          sl[q] = __shfl_down_sync(0xffffffffu, slo[q], o, 16);
+          sh2[q] = __shfl_down_sync(0xffffffffu, shi[q], o, 16);
+        }
+        if (int(lane16) >= o) {
+          pc += pcn;
+#pragma unroll
+          for (int q = 0; q < 3; q++) { plo[q] = fminf(plo[q], pl[q]); phi[q] = fmaxf(phi[q], ph[q]); }
+        }
+        if (int(lane16) + o < 16) {
+          sc += scn;
+#pragma unroll
+          for (int q = 0; q < 3; q++) { slo[q] = fminf(slo[q], sl[q]); shi[q] = fmaxf(shi[q], sh2[q]); }
+        }
+      }
+      // the plane after bin b: left = prefix(b), right = suffix(b + 1)
+      const uint32_t rc = __shfl_down_sync(0xffffffffu, sc, 1, 16);
+      float rlo[3], rhi[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        rlo[q] = __shfl_down_sync(0xffffffffu, slo[q], 1, 16);
+        rhi[q] = __shfl_down_sync(0xffffffffu, shi[q], 1, 16);
+      }
+      unsigned long long key = ~0ull;
+      if (axisOk && lane16 < 15u && pc > 0u && rc > 0u) {
+        const float cost = cadd(cmul(sahHalfArea(plo, phi), float(pc)), cmul(sahHalfArea(rlo, rhi), float(rc)));
+        key = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned long long)(k << 8 | lane16);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o, 16);
+        key = other < key ? other : key;
+      }
+      if (live && lane16 == 0u && key != ~0ull) atomicMin(a.bestKey + slot, key);
+    }
+    __syncthreads();
     for (uint32_t s = tid; s < nSeg; s += T) {
-      const int4 sg = segs[s];
-      const int slot = sg.w;
+      const int slot = segs[s].w;
       int bestAxis = -1, bestSplit = 0;
-      float bestCost = 3.0e38f, bestClo = 0.0f, bestScale = 0.0f;
-      for (int k = 0; k < 3 && slot >= 0; k++) {
-        const float clo = orderedToFloat(a.cbounds[6 * slot + k]), chi = orderedToFloat(a.cbounds[6 * slot + 3 + k]);
-        const float ext = csub(chi, clo);
-        if (!(ext > 0.0f)) continue;
-        const size_t b0 = (size_t(slot) * 3 + k) * KF_TLAS_BINS;
-        float rarea[KF_TLAS_BINS];
-        uint32_t rcnt[KF_TLAS_BINS];
-        float lo3[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi3[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-        uint32_t c = 0;
-        for (int b = KF_TLAS_BINS - 1; b > 0; b--) {
-          for (int q = 0; q < 3; q++) {
-            lo3[q] = fminf(lo3[q], orderedToFloat(a.binBox[6 * (b0 + b) + q]));
-            hi3[q] = fmaxf(hi3[q], orderedToFloat(a.binBox[6 * (b0 + b) + 3 + q]));
-          }
-          c += a.binCount[b0 + b];
-          rarea[b] = c ? sahHalfArea(lo3, hi3) : 0.0f;
-          rcnt[b] = c;
-        }
-        for (int q = 0; q < 3; q++) { lo3[q] = 3.0e38f; hi3[q] = -3.0e38f; }
-        c = 0;
-        for (int b = 0; b + 1 < KF_TLAS_BINS; b++) {  // split after bin b
-          for (int q = 0; q < 3; q++) {
-            lo3[q] = fminf(lo3[q], orderedToFloat(a.binBox[6 * (b0 + b) + q]));
-            hi3[q] = fmaxf(hi3[q], orderedToFloat(a.binBox[6 * (b0 + b) + 3 + q]));
-          }
-          c += a.binCount[b0 + b];
-          if (c == 0 || rcnt[b + 1] == 0) continue;
-          const float cost = cadd(cmul(sahHalfArea(lo3, hi3), float(c)), cmul(rarea[b + 1], float(rcnt[b + 1])));
-          if (cost < bestCost) {
-            bestCost = cost;
-            bestAxis = k;
-            bestSplit = b;
-            bestClo = clo;
-            bestScale = cdiv(float(KF_TLAS_BINS), ext);
-          }
-        }
+      float bestClo = 0.0f, bestScale = 0.0f;
+      const unsigned long long key = slot >= 0 ? __ldcg(a.bestKey + slot) : ~0ull;
+      if (key != ~0ull) {
+        bestAxis = int((key >> 8) & 3ull);
+        bestSplit = int(key & 15ull);
+        bestClo = orderedToFloat(a.cbounds[6 * slot + bestAxis]);
+        bestScale = cdiv(float(KF_TLAS_BINS), csub(orderedToFloat(a.cbounds[6 * slot + 3 + bestAxis]), bestClo));
       }
       a.decision[s] = make_int4(bestAxis, bestSplit, 0, 0);
       a.decisionF[s] = make_float2(bestClo, bestScale);
@@ -649,25 +685,21 @@ __global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs
     };
     blockExclusiveScan(n, a.pre, sScan, goesLeft);
     // ---- children, nodes and segments of the next level ---------------------------------------------
+    // new segments (children of more than one primitive) in the low half, new bin slots (more than two)
+    // in the high half: at most n / 2 and n / 3 of them, n <= 65 536, so one scan carries both
     auto newSegments = [&](uint32_t s) -> uint32_t {
       const int4 sg = segs[s];
-      const uint32_t nLeft = a.pre[sg.z + 1] - a.pre[sg.y], cnt = uint32_t(sg.z - sg.y + 1);
-      return (nLeft > 1 ? 1u : 0u) + (cnt - nLeft > 1 ? 1u : 0u);
+      const uint32_t nLeft = a.pre[sg.z + 1] - a.pre[sg.y], nRight = uint32_t(sg.z - sg.y + 1) - nLeft;
+      return (nLeft > 1 ? 1u : 0u) + (nRight > 1 ? 1u : 0u) + (((nLeft > 2 ? 1u : 0u) + (nRight > 2 ? 1u : 0u)) << 16);
     };
     blockExclusiveScan(nSeg, a.segPre, sScan, newSegments);
-    auto newBinSlots = [&](uint32_t s) -> uint32_t {
-      const int4 sg = segs[s];
-      const uint32_t nLeft = a.pre[sg.z + 1] - a.pre[sg.y], cnt = uint32_t(sg.z - sg.y + 1);
-      return (nLeft > 2 ? 1u : 0u) + (cnt - nLeft > 2 ? 1u : 0u);
-    };
-    blockExclusiveScan(nSeg, segPreBig, sScan, newBinSlots);
     const uint32_t nodeBase = sCount[1];
     for (uint32_t s = tid; s < nSeg; s += T) {
       const int4 sg = segs[s];
       const int lo = sg.y, hi = sg.z;
       const int nLeft = int(a.pre[hi + 1] - a.pre[lo]);
       const int mid = lo + nLeft - 1;
-      uint32_t next = a.segPre[s], nextBig = segPreBig[s];
+      uint32_t next = a.segPre[s] & 0xffffu, nextBig = a.segPre[s] >> 16;
       int4 d = a.decision[s];
       d.z = nLeft;
       d.w = int(next);
@@ -714,9 +746,9 @@ __global__ void __launch_bounds__(KF_TLAS_SAH_THREADS, 1) k_tlas_sah(TlasSahArgs
     }
     __syncthreads();
     if (tid == 0) {
-      sCount[1] = nodeBase + a.segPre[nSeg];
-      sCount[0] = a.segPre[nSeg];
-      sCount[2] = segPreBig[nSeg];
+      sCount[1] = nodeBase + (a.segPre[nSeg] & 0xffffu);
+      sCount[0] = a.segPre[nSeg] & 0xffffu;
+      sCount[2] = a.segPre[nSeg] >> 16;
     }
     { uint32_t* t = vals; vals = valsOther; valsOther = t; }
     { uint32_t* t = segOf; segOf = segOfNext; segOfNext = t; }

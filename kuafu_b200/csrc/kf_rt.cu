@@ -126,6 +126,7 @@ struct BuildState {
   DevBuf<int4> sahSegs, sahDecision;
   DevBuf<float2> sahDecisionF;
   DevBuf<int> sahBounds, sahBinBox;
+  DevBuf<unsigned long long> sahBestKey;
   uint32_t* sortedVals = nullptr;  // valsA or valsB after the sort
   uint64_t* sortedKeys = nullptr;  // keysA or keysB after the sort
   void release() {
@@ -136,6 +137,7 @@ struct BuildState {
     batchGeoms.release(); primGeom.release(); batchCounters.release(); batchBoxes.release();
     sahSegOf.release(); sahBinCount.release(); sahPre.release(); sahSegPre.release(); sahSegs.release();
     sahDecision.release(); sahDecisionF.release(); sahBounds.release(); sahBinBox.release();
+    sahBestKey.release();
   }
 };
 
@@ -317,6 +319,7 @@ static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
   KF_CUDA(ctx, st.sahBounds.ensure(6 * maxSlots));
   KF_CUDA(ctx, st.sahBinCount.ensure(3 * KF_TLAS_BINS * maxSlots));
   KF_CUDA(ctx, st.sahBinBox.ensure(size_t(18) * KF_TLAS_BINS * maxSlots));
+  KF_CUDA(ctx, st.sahBestKey.ensure(maxSlots));
   KF_CUDA(ctx, st.sahDecision.ensure(maxSeg));
   KF_CUDA(ctx, st.sahDecisionF.ensure(maxSeg));
   KF_CUDA(ctx, st.sahPre.ensure(size_t(n) + 1));
@@ -334,6 +337,7 @@ static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
   a.cbounds = st.sahBounds.p;
   a.binCount = st.sahBinCount.p;
   a.binBox = st.sahBinBox.p;
+  a.bestKey = st.sahBestKey.p;
   a.decision = st.sahDecision.p;
   a.decisionF = st.sahDecisionF.p;
   a.pre = st.sahPre.p;

@@ -166,6 +166,18 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
   __shared__ uint32_t sClassBuf[2][2][4];  // per warp: hits, misses
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t round = 0;
+  // The queue entry and hit record of the NEXT round are fetched while this round is shaded: the deal
+  // below needs them before its first barrier, and with the loads issued a round ahead the barrier no
+  // longer waits for memory (ncu, round 2: 3.5 barrier-stall cycles per issued instruction before).
+  uint32_t nextSlot = 0;
+  int nextHit = -1;
+  {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 < count) {
+      nextSlot = queue[i0];
+      nextHit = a.b.hitB[i0];
+    }
+  }
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride, round ^= 1u) {
     uint32_t* sSlot = sSlotBuf[round];
     uint32_t* sQpos = sQposBuf[round];
@@ -177,11 +189,14 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
     {
       const uint32_t i = base + threadIdx.x;
       const bool have = i < count;
-      uint32_t mySlot = 0;
-      int myHit = -1;
-      if (have) {  // two independent streams: the queue entry and the hit record written at its position
-        mySlot = queue[i];
-        myHit = a.b.hitB[i];
+      const uint32_t mySlot = nextSlot;
+      const int myHit = nextHit;
+      {
+        const uint32_t i2 = i + stride;
+        if (i2 < count) {
+          nextSlot = queue[i2];
+          nextHit = a.b.hitB[i2];
+        }
       }
       const uint32_t hitMask = __ballot_sync(0xffffffffu, have && myHit != -1);
       const uint32_t missMask = __ballot_sync(0xffffffffu, have && myHit == -1);
@@ -317,14 +332,27 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[5] = 0;  // occlusion fetch cursor of the next round
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
+  // queue entry and occlusion verdict are fetched a round ahead of the state gathers that depend on them
+  uint32_t nextSlot = 0;
+  int nextOcc = 0;
+  {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 < count) {
+      nextSlot = queue[i0];
+      nextOcc = a.b.hitB[i0];
+    }
+  }
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
     const uint32_t i = base + threadIdx.x;
     const bool valid = i < count;
     bool toNext = false, toShadow = false;
-    uint32_t slot = 0;
+    uint32_t slot = nextSlot;
+    const bool occluded = nextOcc != 0;  // written by k_wf_trace<true> at the queue position
+    if (i + stride < count) {
+      nextSlot = queue[i + stride];
+      nextOcc = a.b.hitB[i + stride];
+    }
     if (valid) {
-      slot = queue[i];
-      const bool occluded = a.b.hitB[i] != 0;  // written by k_wf_trace<true> at the queue position
       const float4 sw = a.b.stateW[slot], sc4 = a.b.stateC[slot], spec = a.b.shadowC[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
       uint32_t seed = __float_as_uint(sw.w);
