@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="spp", choices=["spp", "cameras"])
+    ap.add_argument("--camera-split", default="interleaved", choices=["interleaved", "contiguous"])
     # debugging overrides (a run that uses them is not a bench value; they are echoed in `config`)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
@@ -282,7 +283,8 @@ def run_cameras(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     renderer = host.Renderer(device=local_rank, accumulate=False)
     ncam = renderer.load_scene(cfg["name"], cfg["width"], cfg["height"], cfg["spp"], cfg["depth"])
-    b, e = host.camera_shard(ncam, rank, world)
+    interleaved = args.camera_split == "interleaved"
+    b, e = host.camera_shard(ncam, rank, world)  # (the size of this rank's share is the same either way)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = rt.Context(handle=renderer.device_context())
@@ -300,7 +302,7 @@ def run_cameras(args, rank, world, local_rank):
         renderer.clock_base = i * (spp + 1)
         if ev:
             ev[0].record(stream)
-        renderer.run_range(b, e)
+        renderer.run_shard(rank, world, interleaved)
         if ev:
             ev[1].record(stream)
 
@@ -331,6 +333,12 @@ def run_cameras(args, rank, world, local_rank):
     total_ms, rays_total = float(mx[0]), float(sm[1])
     value = rays_total / (total_ms * 1e-3) / 1e6
     stats = ctx.bvh_stats()
+    # per-rank device time and rays: the cameras of a contiguous range do not see equal amounts of scene
+    per_rank = [tot.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, tot)
+    rank_ms = [float(t[0]) / args.steps for t in per_rank]
+    rank_rays = [float(t[1]) / args.steps for t in per_rank]
 
     # e2e: frames of all ranks end up in pinned host memory on rank 0
     frame_bytes = cfg["width"] * cfg["height"] * 4
@@ -346,7 +354,7 @@ def run_cameras(args, rank, world, local_rank):
         t = time.perf_counter()
         renderer.animate(i)
         renderer.clock_base = i * (spp + 1)
-        renderer.run_range(b, e)
+        renderer.run_shard(rank, world, interleaved)
         ptr, nbytes = ctx.device_buffer(wire.AUX_BGRA8)
         mine = torch.as_tensor(DevBytes(ptr, nbytes), device="cuda")
         if world > 1:
@@ -374,11 +382,12 @@ def run_cameras(args, rank, world, local_rank):
             "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CAMERA_WORKLOAD, **cfg, "cameras": ncam, "parallelism": f"camera-shard x{world}",
+            "config": {"workload": CAMERA_WORKLOAD, **cfg, "cameras": ncam, "parallelism": f"camera-shard x{world} ({args.camera_split})",
                        "cameras_per_gpu": e - b, "l2": "flushed between timed steps (512 MiB memset)",
                        "triangles_instanced": int(stats["instancedTriangles"]), "instances": int(stats["instanceCount"])},
             "per_gpu_mrays": value / world, "rays_per_step": rays_total / args.steps,
             "tlas_rebuilds_rank0": int(stats["tlasRebuilds"]),
+            "rank_ms_per_step": rank_ms, "rank_rays_per_step": rank_rays,
             "e2e": {"value": e2e_rays / e2e_t / 1e6, "unit": "Mrays/s",
                     "h2d_bytes_per_step": 64 * int(stats["instanceCount"]) + (e - b) * 320 + 48 + 2592,
                     "d2h_bytes_per_step": ncam * frame_bytes, "ms_per_step": e2e_t / args.steps * 1e3},
@@ -389,8 +398,26 @@ def run_cameras(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def keep_freed_memory():
+    """Host-process allocator policy for the e2e legs: Camera::downloadLatestFrame returns the frame BY VALUE
+    (the reference's signature), i.e. a fresh 8 MB std::vector per frame, and with glibc's defaults every other
+    such allocation is mmap'ed and page-faulted in again (measured on the box: 5.2 ms vs 1.8 ms per download,
+    alternating).  A host that downloads frames in a loop keeps freed memory instead; SAPIEN-side this is one
+    mallopt call at start-up."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_MMAP_THRESHOLD = -1, -3
+        libc.mallopt(M_MMAP_THRESHOLD, 1 << 30)
+        libc.mallopt(M_TRIM_THRESHOLD, 1 << 30)
+        return True
+    except OSError:
+        return False
+
+
 def main():
     args = parse_args()
+    keep_freed_memory()
     cfg = effective_config(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

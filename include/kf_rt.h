@@ -267,6 +267,11 @@ KFRT_API int kfrtReduceNccl(KfrtContext* ctx, void* ncclComm, int root);
  * BGRA, sRGB-encoded, alpha 255; synchronises the context's stream. */
 KFRT_API int kfrtDownloadBGRA8(KfrtContext* ctx, uint32_t camera, uint8_t* dst, size_t nbytes);
 KFRT_API int kfrtDownloadAux(KfrtContext* ctx, uint32_t camera, int kind, void* dst, size_t nbytes);
+/* The same frame without the copy: a pointer into the context's pinned staging buffer, which kfrtResolve
+ * starts filling asynchronously the moment the frame is encoded.  Waits for that copy only; the bytes
+ * stay valid until the next kfrtResolve / kfrtRender of a different size.  (A host that returns the frame
+ * by value, like Camera::downloadLatestFrame, builds its vector from this in one pass.) */
+KFRT_API int kfrtMapBGRA8(KfrtContext* ctx, uint32_t camera, const uint8_t** bytes, size_t* nbytes);
 /* Device address and size (all cameras, camera-major) of an output buffer, for host plumbing that
  * wants to run a collective or a copy on it without a host round trip. */
 KFRT_API int kfrtGetDeviceBuffer(KfrtContext* ctx, int kind, void** devicePtr, size_t* nbytes);

@@ -54,6 +54,10 @@ KFC_API int kfcRunAll(KfcRenderer* r);
  * cameras [begin, end) in one launch. */
 KFC_API int kfcCameraShard(int nCameras, int rank, int world, int* begin, int* end);
 KFC_API int kfcRunRange(KfcRenderer* r, int begin, int end);
+/* Kuafu::cameraShardIndices() + Kuafu::run() on those recipe cameras in one launch; the indices rendered are
+ * returned in `indices` (capacity entries), their number in *count.  After it, kfcDownloadFrame(camera) works
+ * for the cameras rendered. */
+KFC_API int kfcRunShard(KfcRenderer* r, int rank, int world, int interleaved, int* indices, int capacity, int* count);
 /* Scene::setEnvironmentMap(path) (a .ktx cube map) on the current scene. */
 KFC_API int kfcSetEnvironmentMap(KfcRenderer* r, const char* path);
 /* The facade's texture / cube-map file readers (image_io.hpp), for the reader tests: dimensions always,

@@ -911,7 +911,7 @@ int kfrtSetLights(KfrtContext* ctx, const KfrtDirectionalLight* directional, con
         pv[i][4 * j + r] = acc;
       }
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->alProjView.p, pv, sizeof(pv), cudaMemcpyHostToDevice, ctx->stream));
-  KF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // (the sources are pageable stack memory: cudaMemcpyAsync has staged them before it returns)
   ctx->nLightSlots = slots;
   return KFRT_OK;
 }
@@ -1603,6 +1603,18 @@ int kfrtDownloadAux(KfrtContext* ctx, uint32_t camera, int kind, void* dst, size
 
 int kfrtDownloadBGRA8(KfrtContext* ctx, uint32_t camera, uint8_t* dst, size_t nbytes) {
   return kfrtDownloadAux(ctx, camera, KFRT_AUX_BGRA8, dst, nbytes);
+}
+
+int kfrtMapBGRA8(KfrtContext* ctx, uint32_t camera, const uint8_t** bytes, size_t* nbytes) {
+  KF_CHECK_CTX(ctx);
+  if (!bytes || !nbytes) KF_FAIL(ctx, KFRT_ERR_INVALID, "null out pointer");
+  if (!ctx->rendered || !ctx->bgraStaged) KF_FAIL(ctx, KFRT_ERR_INVALID, "no resolved frame to map (kfrtResolve first)");
+  if (camera >= ctx->nCams) KF_FAIL(ctx, KFRT_ERR_INVALID, "bad camera index");
+  KF_CUDA(ctx, cudaEventSynchronize(ctx->stagedEvent));
+  const size_t np = size_t(ctx->width) * ctx->height;
+  *bytes = ctx->bgraStage + camera * np * 4;
+  *nbytes = np * 4;
+  return KFRT_OK;
 }
 
 int kfrtGetDeviceBuffer(KfrtContext* ctx, int kind, void** devicePtr, size_t* nbytes) {

@@ -39,6 +39,7 @@ def load():
     lib.kfcRunAll.argtypes = [vp]
     lib.kfcCameraShard.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.kfcRunRange.argtypes = [vp, i32, i32]
+    lib.kfcRunShard.argtypes = [vp, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(i32)]
     lib.kfcSetEnvironmentMap.argtypes = [vp, C.c_char_p]
     lib.kfcReadTexture.argtypes = [C.c_char_p, C.POINTER(u32), C.POINTER(u32), vp, sz]
     lib.kfcReadKtxCube.argtypes = [C.c_char_p, C.POINTER(u32), vp, sz]
@@ -174,6 +175,15 @@ class Renderer:
     def run_range(self, begin, end):
         """Kuafu::run() on the recipe cameras [begin, end) in one launch (camera-batch shard)."""
         self._ck(self.lib.kfcRunRange(self.h, begin, end), "kfcRunRange")
+
+    def run_shard(self, rank, world, interleaved=True):
+        """Kuafu::run() on this rank's share of the recipe cameras (Kuafu::cameraShardIndices); returns the
+        camera indices rendered, in device slot order."""
+        cap = self.lib.kfcNumCameras(self.h)
+        idx = (C.c_int * max(cap, 1))()
+        n = C.c_int()
+        self._ck(self.lib.kfcRunShard(self.h, rank, world, int(interleaved), idx, cap, C.byref(n)), "kfcRunShard")
+        return [int(idx[k]) for k in range(n.value)]
 
     def set_environment_map(self, path):
         self._ck(self.lib.kfcSetEnvironmentMap(self.h, str(path).encode()), "kfcSetEnvironmentMap")

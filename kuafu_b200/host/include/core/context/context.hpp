@@ -67,6 +67,7 @@ class KUAFU_API Context {
   uint64_t mSerial = 0;
   std::vector<Camera*> mLastCameras;
   std::vector<float> mLastTransforms;
+  std::vector<uint8_t> mLastLights;  // the light blocks last uploaded
   Scene* mUploadedScene = nullptr;
   bool mSharded = false, mDeferResolve = false;
   uint32_t mSampleBegin = 0, mSampleEnd = 0;

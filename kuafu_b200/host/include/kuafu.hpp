@@ -29,6 +29,10 @@ class KUAFU_API Kuafu {
   /// at most one.  Every process holds the whole scene and refits its own top level once per run();
   /// no collective is involved.
   static std::pair<size_t, size_t> cameraShard(size_t nCameras, int rank, int world);
+  /// The same split as a list of camera indices; interleaved: rank, rank + world, rank + 2 world, ...
+  /// instead of a contiguous range.  Neighbouring cameras of a rig see similar amounts of scene, so an
+  /// interleaved split balances the ranks where a contiguous one leaves the busiest views on one GPU.
+  static std::vector<size_t> cameraShardIndices(size_t nCameras, int rank, int world, bool interleaved);
 
   [[nodiscard]] bool isRunning() const;
 

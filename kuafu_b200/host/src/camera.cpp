@@ -2,6 +2,8 @@
 // reference's sign conventions (negative [1][1]: image y grows downwards), view = lookAt.
 #include "core/camera.hpp"
 
+#include <cstdlib>
+
 #include "core/context/context.hpp"
 #include "kf_rt.h"
 
@@ -128,7 +130,16 @@ std::vector<uint8_t> Camera::downloadAuxBytes(int kind, size_t bytesPerPixel) {
 
 std::vector<uint8_t> Camera::downloadLatestFrame() {
   KF_ASSERT(mFrames.valid, "Invalid call to Camera::downloadLatestFrame");
-  if (mFrames.owner && mFrames.serial == mFrames.owner->mSerial) return downloadAuxBytes(KFRT_AUX_BGRA8, 4);
+  if (mFrames.owner && mFrames.serial == mFrames.owner->mSerial) {
+    // the frame is already on its way to pinned host memory (kfrtResolve started the copy): the vector
+    // the reference's signature returns is built from it in one pass
+    Context* ctx = mFrames.owner;
+    const uint8_t* bytes = nullptr;
+    size_t n = 0;
+    if (kfrtMapBGRA8(ctx->getDevice(), mFrames.slot, &bytes, &n) == KFRT_OK && n == size_t(mWidth) * mHeight * 4)
+      return std::vector<uint8_t>(bytes, bytes + n);
+    return downloadAuxBytes(KFRT_AUX_BGRA8, 4);  // rendered but not resolved (deferred resolve): the device copy
+  }
   KF_ASSERT(!mFrames.stash.empty(), "Invalid call to Camera::downloadLatestFrame");
   return mFrames.stash;
 }

@@ -107,6 +107,20 @@ int kfcRunRange(KfcRenderer* r, int begin, int end) {
   });
 }
 
+int kfcRunShard(KfcRenderer* r, int rank, int world, int interleaved, int* indices, int capacity, int* count) {
+  return guarded([&] {
+    const auto idx = Kuafu::cameraShardIndices(r->cameras.size(), rank, world, interleaved != 0);
+    if (int(idx.size()) > capacity) throw std::runtime_error("kfcRunShard: index buffer too small");
+    std::vector<Camera*> cams;
+    for (size_t k = 0; k < idx.size(); k++) {
+      cams.push_back(r->cameras.at(idx[k]));
+      indices[k] = int(idx[k]);
+    }
+    *count = int(idx.size());
+    if (!cams.empty()) r->renderer->run(cams);
+  });
+}
+
 int kfcSetEnvironmentMap(KfcRenderer* r, const char* path) {
   return guarded([&] { r->renderer->getScene()->setEnvironmentMap(path); });
 }

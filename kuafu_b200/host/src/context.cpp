@@ -90,6 +90,7 @@ void Context::update() {
     pConfig->mMaxGeometryChanged = pConfig->mMaxGeometryInstancesChanged = pConfig->mMaxTexturesChanged = false;
   }
   if (mUploadedScene != &s) {  // switching scenes re-uploads everything ("this is heavy")
+    mLastLights.clear();
     check(kfrtClearGeometries(mRt), "kfrtClearGeometries");
     for (auto& g : s.mGeometries)
       if (g) g->initialized = false;
@@ -161,10 +162,19 @@ void Context::update() {
   }
 
   s.packLights();
-  check(kfrtSetLights(mRt, reinterpret_cast<const KfrtDirectionalLight*>(&s.mWire.directional),
-                      reinterpret_cast<const KfrtPointLights*>(&s.mWire.points),
-                      reinterpret_cast<const KfrtActiveLights*>(&s.mWire.actives)),
-        "kfrtSetLights");
+  {  // the light blocks are rewritten every frame like the reference's UBOs, uploaded when they changed
+    std::vector<uint8_t> now(sizeof(s.mWire.directional) + sizeof(s.mWire.points) + sizeof(s.mWire.actives));
+    std::memcpy(now.data(), &s.mWire.directional, sizeof(s.mWire.directional));
+    std::memcpy(now.data() + sizeof(s.mWire.directional), &s.mWire.points, sizeof(s.mWire.points));
+    std::memcpy(now.data() + sizeof(s.mWire.directional) + sizeof(s.mWire.points), &s.mWire.actives, sizeof(s.mWire.actives));
+    if (now != mLastLights) {
+      check(kfrtSetLights(mRt, reinterpret_cast<const KfrtDirectionalLight*>(&s.mWire.directional),
+                          reinterpret_cast<const KfrtPointLights*>(&s.mWire.points),
+                          reinterpret_cast<const KfrtActiveLights*>(&s.mWire.actives)),
+            "kfrtSetLights");
+      mLastLights.swap(now);
+    }
+  }
 
   global::frameCount = predictFrameCount();
 }

@@ -43,6 +43,18 @@ std::pair<size_t, size_t> Kuafu::cameraShard(size_t nCameras, int rank, int worl
   return {nCameras * r / w, nCameras * (r + 1) / w};
 }
 
+std::vector<size_t> Kuafu::cameraShardIndices(size_t nCameras, int rank, int world, bool interleaved) {
+  KF_ASSERT(world > 0 && rank >= 0 && rank < world, "cameraShardIndices: rank must lie in [0, world)");
+  std::vector<size_t> out;
+  if (interleaved) {
+    for (size_t c = size_t(rank); c < nCameras; c += size_t(world)) out.push_back(c);
+  } else {
+    const auto range = cameraShard(nCameras, rank, world);
+    for (size_t c = range.first; c < range.second; c++) out.push_back(c);
+  }
+  return out;
+}
+
 std::vector<uint8_t> Kuafu::downloadLatestFrame(Camera* cam) {
   KF_ASSERT(cam, "Invalid call to Camera::downloadLatestFrame");
   return cam->downloadLatestFrame();

@@ -41,6 +41,7 @@ def load():
         "kfrtBuildTlas": [vp], "kfrtRefitTlas": [vp, vp, u32], "kfrtGetBvhStats": [vp, vp],
         "kfrtRender": [vp, vp, u32, u32, u32, vp, u32, u32, u32], "kfrtResolve": [vp],
         "kfrtReduceNccl": [vp, vp, i32], "kfrtDownloadBGRA8": [vp, u32, vp, sz],
+        "kfrtMapBGRA8": [vp, u32, C.POINTER(vp), C.POINTER(sz)],
         "kfrtDownloadAux": [vp, u32, i32, vp, sz],
         "kfrtGetDeviceBuffer": [vp, i32, C.POINTER(vp), C.POINTER(sz)],
         "kfrtSetDetailCounters": [vp, i32], "kfrtGetCounters": [vp, vp],
@@ -195,6 +196,15 @@ class Context:
         out = np.empty((h, w, 4), "u1")
         self._ck(self.lib.kfrtDownloadBGRA8(self.h, camera, _ptr(out), out.nbytes))
         return out
+
+    def map_bgra8(self, camera=0):
+        """Zero-copy view of the encoded frame in the context's pinned staging buffer (valid until the next
+        resolve)."""
+        _, h, w = self.shape
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.kfrtMapBGRA8(self.h, camera, C.byref(p), C.byref(n)))
+        assert n.value == h * w * 4
+        return np.frombuffer((C.c_ubyte * n.value).from_address(p.value), "u1").reshape(h, w, 4)
 
     def download_aux(self, kind, camera=0, out=None):
         _, h, w = self.shape

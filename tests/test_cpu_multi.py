@@ -117,6 +117,33 @@ def test_camera_shard_ranges_partition():
         host.camera_shard(8, 2, 2)
 
 
+def test_interleaved_camera_shard_covers_the_batch():
+    """Kuafu::cameraShardIndices through a host-only renderer: rank, rank + world, ... ; every camera once."""
+    from kuafu_b200 import host
+    import ctypes as C
+    r = host.Renderer(device=None)
+    ncam = r.load_scene("articulated", 32, 32, 1, 0, 7)
+    lib = host.load()
+    for world in (1, 2, 3):
+        seen = []
+        for rank in range(world):
+            for inter in (0, 1):
+                idx = (C.c_int * ncam)()
+                n = C.c_int()
+                # host-only: the indices come back, then run() refuses to render (no device, no CPU fallback)
+                rc = lib.kfcRunShard(r.h, rank, world, inter, idx, ncam, C.byref(n))
+                assert rc != 0 and b"no CUDA device" in lib.kfcLastError() or n.value == 0
+                got = [idx[k] for k in range(n.value)]
+                if inter:
+                    assert got == list(range(rank, ncam, world))
+                    seen += got
+                else:
+                    b, e = host.camera_shard(ncam, rank, world)
+                    assert got == list(range(b, e))
+        assert sorted(seen) == list(range(ncam))
+    r.close()
+
+
 def test_gloo_world2_spp_shard_reduce():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

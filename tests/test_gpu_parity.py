@@ -75,6 +75,23 @@ def test_spot_light_without_texture(rt, orc_mod, fov_deg, softness):
     ctx.close()
 
 
+def test_mapped_frame_equals_the_downloaded_frame(rt, orc_mod):
+    """kfrtMapBGRA8 (the pinned staging copy kfrtResolve starts) hands out the bytes kfrtDownloadBGRA8
+    copies, for every camera of a batch, and the oracle's encode of the same sums."""
+    sc = pyscene.small_scene(seed=12, w=64, h=40, spp=2, depth=3, lights="dir")
+    sc.cams = [sc.cams[0], pyscene.camera([-10.0, 3.0, 6.0], [0.7, -0.2, -0.4], [0, 0, 1], sc.w, sc.h)]
+    ctx, orc = _pair(sc, rt, orc_mod)
+    got, ref = parity.render_both(sc, ctx, orc)
+    ctx.resolve()
+    rgba = np.zeros_like(got["sum"])
+    want = orc.resolve(got["sum"], rgba, 2, -1)
+    for cam in range(2):
+        mapped = ctx.map_bgra8(cam).copy()
+        assert np.array_equal(mapped, ctx.download_bgra8(cam))
+        assert np.array_equal(mapped, want[cam])
+    ctx.close()
+
+
 def test_brute_force_oracle_agrees(rt, orc_mod):
     """BVH layout must not change the answer: GPU (8-wide LBVH) == oracle brute force over all triangles."""
     sc = pyscene.small_scene(seed=5, w=64, h=48, spp=1, depth=3, lights="dir", stacks=6, slices=8)
