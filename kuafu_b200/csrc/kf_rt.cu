@@ -215,8 +215,6 @@ struct KfrtContext {
   // wavefront scheduler state
   int numSMs = 148;
   size_t batchSlotTarget = size_t(64) << 20;  // measured on config 3: 32 Mi -> 64 Mi slots +0.8 %, 128 Mi no further gain
-  int refillIdle = KF_REFILL_IDLE;
-  int instPeriod = KF_INST_PERIOD;
   bool traceLog = false;  // KFRT_TRACE_LOG=1: per-launch ray count and time of every traversal stage on stderr
   size_t wfSlots = 0;
   bool wfMulti = false;
@@ -682,8 +680,6 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  if (const char* e = std::getenv("KFRT_REFILL_IDLE")) ctx->refillIdle = std::max(1, std::atoi(e));
-  if (const char* e = std::getenv("KFRT_INST_PERIOD")) ctx->instPeriod = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
@@ -1344,8 +1340,6 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       te.counters = a.counters;
       te.rayCounter = 1;
       te.detailBase = 4;
-      te.refillIdle = ctx->refillIdle;
-      te.instPeriod = ctx->instPeriod;
       stageMark(ctx, KFRT_STAGE_TRACE_CLOSEST);
       logBegin();
       launchTrace(ctx, te, false, d != 0);

@@ -31,6 +31,9 @@ namespace kf {
 #ifndef KF_STACK_SHARED
 #define KF_STACK_SHARED 8  // stack entries per lane kept in shared memory (8 KB per block)
 #endif
+// Both are compile-time constants (as kernel arguments they cost a constant load and a compare per
+// iteration: 0.4 % of the stage); re-measured in round 2 after the node test got cheaper: 6 / 10 / 12 idle
+// lanes and periods 1 / 3 all lose 0.2 - 3 %.
 #define KF_INST_PERIOD 2  // measured on config 3: 1 -> 2 takes 2.8 % off the closest-hit stage, 4 loses it again
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
 
@@ -52,8 +55,6 @@ struct TraceArgs {
   unsigned long long* counters;
   int rayCounter;            // counters[] index that receives the number of rays of this stage
   int detailBase;            // counters[] index of (nodes, tris, insts) for detail accounting
-  int refillIdle;            // refill a warp once this many of its lanes are without a ray
-  int instPeriod;            // the instance phase runs every instPeriod-th iteration (see there)
 };
 
 // Closest hit (ANY == false) or first hit (ANY == true; TerminateOnFirstHit | Opaque |
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     // ---- refill: lanes without a ray take consecutive queue positions -------------------------
     const uint32_t idle = __ballot_sync(0xffffffffu, !active);
     if (idle) {
-      if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= a.refillIdle)) {
+      if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= KF_REFILL_IDLE)) {
         const uint32_t want = uint32_t(__popc(idle));
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(a.fetch, want);
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     // ---- instance phase (top level): the nearest pending child is an InstNode ------------------
     // Few lanes want it in any one iteration, yet the whole warp pays its ~130 instructions; taking
     // it only every instPeriod-th iteration lets the requests pile up (a waiting lane idles).
-    if (++iter >= a.instPeriod) iter = 0;
+    static_assert(KF_INST_PERIOD == 2, "the phase counter below is a parity bit");
+    iter ^= 1;
     if (iter == 0 && active && !inBlas && (ng.y & 0xff000000u)) {
       const uint32_t hits = ng.y;
       const int p = 31 - __clz(hits);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
       if (!((hits >> (8 + cslot)) & 1u)) {
         ng.y &= ~(1u << p);
         const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
-        const uint4* ip = reinterpret_cast<const uint4*>(nodes + ng.x + rel);
+        const uint4* ip = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));  // 32-bit index sum: one wide multiply-add
         const uint4 w4 = __ldg(ip + 4);
         if (DETAIL) tc.insts++;
         // re-test the instance's own world box against what is now the closest hit
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
         if (ng.y & 0xff000000u) push(ng);
         const uint32_t rel = __popc(hits & 0xffu & ((1u << cslot) - 1u));
         uint32_t childBase, primBase, imask, triMask;
-        const uint32_t miss = intersectNode(nodes + ng.x + rel, r, tmin, hit.t, childBase, primBase, imask, triMask);
+        const uint32_t miss = intersectNode(nodes + (ng.x + rel), r, tmin, hit.t, childBase, primBase, imask, triMask);
         if (DETAIL) tc.nodes++;
         if (DETAIL && !inBlas) tc.tlasNodes++;
         const uint32_t inner = sMask.perm[r.octinv][imask & ~miss];
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
     if (active && !finished && (tg.y & 0xffffu)) {
       const int b = __ffs(tg.y) - 1;
       tg.y &= tg.y - 1;
-      const float4* tp = reinterpret_cast<const float4*>(tris + tg.x + __popc((tg.y >> 16) & ((1u << b) - 1u)));
+      const float4* tp = reinterpret_cast<const float4*>(tris + (tg.x + __popc((tg.y >> 16) & ((1u << b) - 1u))));
       const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
       if (DETAIL) tc.tris++;
       // Moller-Trumbore, fused arithmetic, same expressions as oracle intersectTri()
