@@ -405,6 +405,8 @@ def keep_freed_memory():
     alternating).  A host that downloads frames in a loop keeps freed memory instead; SAPIEN-side this is one
     mallopt call at start-up."""
     import ctypes
+    if os.environ.get("KFB_DEFAULT_MALLOC"):  # A/B switch for the measurement in DESIGN.md §6
+        return False
     try:
         libc = ctypes.CDLL("libc.so.6")
         M_TRIM_THRESHOLD, M_MMAP_THRESHOLD = -1, -3
