@@ -85,39 +85,44 @@ KF_D void countAdd(unsigned long long* c, bool pred) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// One thread per pixel slot, looping over the samples of the batch: the pixel's seed hash (shared by all
+// samples, rgen:23) is made once and its jitter stream advanced two draws per sample instead of being
+// re-hashed and skipped ahead for every (sample, pixel) pair, and the queue comes out as runs of 256
+// consecutive pixels of one sample followed by the same pixels of the next sample -- rays that walk the
+// same part of the hierarchy sit next to each other in the first traversal stage.
 __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
-  const uint32_t total = a.slotsPerSample * a.batchCount;
   const uint32_t stride = gridDim.x * blockDim.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.b.counts[1] = 0;
     a.b.counts[2] = 0;
     a.b.counts[3] = 0;
   }
-  for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-    const uint32_t slot = base + threadIdx.x;
-    bool valid = slot < total;
-    uint32_t cam = 0, x = 0, y = 0, s = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < a.slotsPerSample; base += stride) {
+    const uint32_t pixelSlot = base + threadIdx.x;
+    bool valid = pixelSlot < a.slotsPerSample;
+    uint32_t cam = 0, x = 0, y = 0;
     if (valid) {
-      s = slot / a.slotsPerSample;
-      slotToPixel(a, slot - s * a.slotsPerSample, cam, x, y);
+      slotToPixel(a, pixelSlot, cam, x, y);
       valid = x < a.w && y < a.h;
     }
-    if (valid) {
-      const uint32_t i = a.batchBegin + s;  // global sample index
-      const uint32_t mapping = y * a.w + x;
-      uint32_t seed = tea(mapping, a.clockBase);
-      // the pixel-jitter stream is shared by all samples of the pixel (rgen:30-37): skip the two draws of
-      // each of the samples < i, in O(log i) instead of 2 i dependent steps
-      seed = lcgSkip(seed, 2u * i);
-      uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
-      V3 o, d;
-      cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);
-      a.b.rayO[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-      a.b.rayD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-      a.b.stateW[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(raySeed));
-      a.b.stateC[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const uint32_t mapping = y * a.w + x;
+    // the pixel-jitter stream is shared by all samples of the pixel (rgen:30-37): skip the two draws of
+    // each sample before this batch once, then two draws per sample
+    uint32_t seed = valid ? lcgSkip(tea(mapping, a.clockBase), 2u * a.batchBegin) : 0u;
+    for (uint32_t s = 0; s < a.batchCount; s++) {
+      const uint32_t slot = s * a.slotsPerSample + pixelSlot;
+      if (valid) {
+        const uint32_t i = a.batchBegin + s;  // global sample index
+        uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
+        V3 o, d;
+        cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);  // draws the sample's two jitter numbers from seed
+        a.b.rayO[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+        a.b.rayD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        a.b.stateW[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(raySeed));
+        a.b.stateC[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      queueAppend(a.b.queue[0], a.b.counts + 0, valid, slot);
     }
-    queueAppend(a.b.queue[0], a.b.counts + 0, valid, slot);
   }
 }
 

@@ -96,6 +96,7 @@ def test_refit_quality_watch_rebuilds_without_changing_hits(mods):
         r.animate(frame)
         r.clock_base = 7
         r.run()
+        r.download_frame(0)  # a renderer loop looks at its frames; the watch reads its area sum back asynchronously
     assert int(ctx.bvh_stats()["tlasRebuilds"]) >= 1
     ws = r.wire_scene()
     orc = oracle.Oracle()

@@ -70,6 +70,7 @@ def test_config5_full_scale_after_motion(mods):
         r.animate(frame)
         r.clock_base = 40 + frame
         r.run_all()
+        r.download_frame(frame % 64)  # like a consumer of the frames (the quality watch reads back asynchronously)
     stats = ctx.bvh_stats()
     assert int(stats["instanceCount"]) == 2049
     assert int(stats["tlasRebuilds"]) >= 1, "the quality watch never rebuilt the top level: only the refit path was checked"
