@@ -54,6 +54,30 @@ def test_config3_full_frame_hit_buffers(mods):
     r.close()
 
 
+@pytest.mark.parametrize("name,w,h,ncams", [("spheres", 800, 600, 1), ("cornell", 1024, 1024, 1), ("active", 1280, 720, 2)])
+def test_configs_1_2_4_at_their_own_resolution(mods, name, w, h, ncams):
+    """Configs 1, 2 and 4 at the resolution BASELINE words them with (config 4: both cameras of the stereo
+    pair), sample 0 of every pixel through the facade against the oracle: hit ids, t and depth bits, albedo /
+    normal, segmentation = instance id (config 4's extra outputs), ray counts and radiance."""
+    host, rt, oracle = mods
+    r = host.Renderer(device=0, accumulate=False)
+    assert r.load_scene(name, 0, 0, 1) == ncams
+    ws = r.wire_scene()
+    assert (ws.w, ws.h) == (w, h)
+    r.clock_base = 9
+    r.run_all()
+    orc = oracle.Oracle()
+    orc.load(ws)
+    for cam in range(ncams):
+        got = _facade_buffers(r, cam)
+        ref = orc.render(np.array(ws.cams[cam:cam + 1]), w, h, ws.pc, clock_base=9)
+        parity.assert_hits_bit_exact(got, ref)
+        assert np.array_equal(r.download_aux(wire.AUX_SEGMENTATION, cam), ref["hit_ids"][0][..., 0])
+        st = parity.radiance_stats(got["sum"], ref["sum"], 1)
+        assert st["frac_gt_1e-3"] < 0.02 and st["mean_rel_diff"] < 2e-3, (cam, st)
+    r.close()
+
+
 def test_config5_full_scale_after_motion(mods):
     """Config 5 as BASELINE words it: 64 chains x 32 links + floor = 2 049 instances (10 035 202 instanced
     triangles), 64 cameras x 512x512, every transform rewritten each frame -> kfrtRefitTlas inside
