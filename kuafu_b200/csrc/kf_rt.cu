@@ -189,6 +189,7 @@ struct KfrtContext {
   bool tlasBuildPending = false, tlasAreaPending = false;
   float tlasAreaAtBuild = 0.0f;
   uint32_t tlasBlasDepth = 0;  // deepest bottom level among the instances of the last build
+  bool tlasSahOptIn = false;   // k_tlas_sah may use its large dynamic shared memory on this device
   uint64_t tlasRebuilds = 0;
 
   // outputs
@@ -340,7 +341,17 @@ static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
   a.decisionF = st.sahDecisionF.p;
   a.pre = st.sahPre.p;
   a.segPre = st.sahSegPre.p;
-  k_tlas_sah<<<1, KF_TLAS_SAH_THREADS, 0, ctx->stream>>>(a);
+  size_t shared = 0;
+  a.inShared = 0;
+  if (n <= KF_TLAS_SHARED_MAX) {
+    shared = tlasSahSharedBytes(n);
+    if (!ctx->tlasSahOptIn) {  // opt in to more than 48 KB of dynamic shared memory, once per context's device
+      KF_CUDA(ctx, cudaFuncSetAttribute(k_tlas_sah, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tlasSahSharedBytes(KF_TLAS_SHARED_MAX))));
+      ctx->tlasSahOptIn = true;
+    }
+    a.inShared = 1;
+  }
+  k_tlas_sah<<<1, KF_TLAS_SAH_THREADS, shared, ctx->stream>>>(a);
   KF_CUDA(ctx, cudaGetLastError());
   st.sortedVals = st.valsA.p;
   return KFRT_OK;
