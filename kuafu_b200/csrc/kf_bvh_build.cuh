@@ -2,11 +2,10 @@
 // VkAccelerationStructureKHR BLAS/TLAS (reference src/core/rt/rt.cpp:142-370 build + compaction,
 // :372-495 per-frame TLAS update).
 //
-// Pipeline (all kernels here; the host only sequences launches):
-//   primitive boxes -> scene box (ordered-int atomics) -> 63-bit Morton keys -> LSD radix sort
-//   -> Karras LBVH hierarchy -> bottom-up boxes (atomic arrival counters)
-//   -> level-by-level collapse into 8-wide nodes (largest-area-first expansion, leaves <= 2 prims,
-//      octant slot assignment, 8-bit quantisation) -> triangles re-laid in leaf order.
+// Here: the pieces both levels share (Morton keys, LSD radix sort, Karras hierarchy, bottom-up boxes,
+// collapse of a binary hierarchy into quantised 8-wide nodes) and everything of the top level (exact
+// instance boxes, binned-SAH hierarchy in one launch, collapse in one launch, instance records, refit).
+// The bottom level is built for all geometries at once by kf_blas_batch.cuh on top of these pieces.
 // Refit keeps the binary topology and the slot assignment, recomputes boxes bottom-up and
 // re-quantises every wide node.
 #pragma once
@@ -878,7 +877,7 @@ struct CollapseArgs {
   int* wideBinary;            // wide node -> binary internal node it collapses
   int* wideMembers;           // 8 member codes per wide node (slot order), for refit
   uint32_t* counters;         // [0] wide nodes allocated, [1] leaf primitives allocated,
-                              // [2], [3] = [lo, hi) of the level being collapsed (k_next_level),
+                              // [2], [3] = [lo, hi) of the level being collapsed,
                               // [4] = levels collapsed so far = depth of the wide tree
   uint32_t* slotOfInst;       // top level only: instance -> index of its InstNode in outNodes
 };

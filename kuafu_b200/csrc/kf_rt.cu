@@ -302,10 +302,6 @@ static int radixSort(KfrtContext* ctx, BuildState& st, uint32_t n, int keyBits =
   return KFRT_OK;
 }
 
-// Builds the wide BVH over st.primBox[0..n) (already filled, with st.sceneBox).  On return
-// st.outNodes[0..nWide) and st.outPrim[0..n) are valid.
-// tlas: top-level layout -- every instance becomes an InstNode slot inside outNodes (st.slotOfInst),
-// so the array holds up to n real nodes plus n instance slots.
 // Binary hierarchy over the instance boxes by top-down binned SAH: one launch of k_tlas_sah
 // (kf_bvh_build.cuh), no host round trip, no stream synchronisation.  It is built when the instance
 // set changes and when the refit watch trips (per-frame motion is the refit).
@@ -357,19 +353,18 @@ static int sahTopLevelHierarchy(KfrtContext* ctx, BuildState& st, uint32_t n) {
   return KFRT_OK;
 }
 
-// Scratch of a build over n primitives (DevBuf::ensure only ever grows a buffer).
-static int reserveBuild(KfrtContext* ctx, BuildState& st, uint32_t n, bool tlas) {
-  const size_t maxNodes = (tlas ? size_t(2) : size_t(1)) * std::max<uint32_t>(n, 1) + 1;
+// Scratch of a top-level build over n instances: up to n real nodes plus n instance slots in the wide array.
+static int reserveTopLevel(KfrtContext* ctx, BuildState& st, uint32_t n) {
+  const size_t maxNodes = size_t(2) * std::max<uint32_t>(n, 1) + 1;
   KF_CUDA(ctx, st.primBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
   KF_CUDA(ctx, st.sceneBox.ensure(6));
-  KF_CUDA(ctx, st.outNodes.ensure(maxNodes));
   KF_CUDA(ctx, st.outPrim.ensure(n));
   KF_CUDA(ctx, st.wideMembers.ensure(size_t(8) * maxNodes));
   KF_CUDA(ctx, st.wideBinary.ensure(maxNodes));
   KF_CUDA(ctx, st.counters.ensure(5));
   KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * std::max<uint32_t>(n, 1)));
-  if (tlas) KF_CUDA(ctx, st.slotOfInst.ensure(std::max<uint32_t>(n, 1)));
-  if ((tlas && n == 1) || (!tlas && n <= KF_LEAF_MAX)) return KFRT_OK;
+  KF_CUDA(ctx, st.slotOfInst.ensure(std::max<uint32_t>(n, 1)));
+  if (n == 1) return KFRT_OK;
   KF_CUDA(ctx, st.hist.ensure(size_t(256) * gridFor(n, KF_SORT_TILE)));
   KF_CUDA(ctx, st.keysA.ensure(n));
   KF_CUDA(ctx, st.keysB.ensure(n));
@@ -1045,7 +1040,7 @@ static int buildTopLevel(KfrtContext* ctx, bool wait) {
   }
   BuildState& st = ctx->tlasBuild;
   st.n = n;
-  rc = reserveBuild(ctx, st, n, true);
+  rc = reserveTopLevel(ctx, st, n);
   if (rc) return rc;
   const size_t maxNodes = size_t(2) * n + 1;
   KF_CUDA(ctx, ctx->tlasNodes.ensure(maxNodes));
