@@ -1259,10 +1259,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     ctx->gridTrace[1] = persistentGrid(ctx, k_wf_trace<false, true>, 128);
     ctx->gridTrace[2] = persistentGrid(ctx, k_wf_trace<true, false>, 128);
     ctx->gridTrace[3] = persistentGrid(ctx, k_wf_trace<true, true>, 128);
-    ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, 128);
-    ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, 128);
-    ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, 128);
-    ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true>, 128);
+    ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, KF_SHADE_THREADS);
+    ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, KF_SHADE_THREADS);
+    ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, KF_SHADE_THREADS);
+    ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true>, KF_SHADE_THREADS);
     ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow_resolve<false, false>, 128);
     ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow_resolve<false, true>, 128);
     ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow_resolve<true, false>, 128);
@@ -1353,10 +1353,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       logEnd("closest", depth, te.count);
       stageMark(ctx, KFRT_STAGE_SHADE);
       switch (variant) {
-        case 0: k_wf_shade<false, false><<<ctx->gridShade[0], 128, 0, st>>>(a, q, depth); break;
-        case 1: k_wf_shade<false, true><<<ctx->gridShade[1], 128, 0, st>>>(a, q, depth); break;
-        case 2: k_wf_shade<true, false><<<ctx->gridShade[2], 128, 0, st>>>(a, q, depth); break;
-        default: k_wf_shade<true, true><<<ctx->gridShade[3], 128, 0, st>>>(a, q, depth); break;
+        case 0: k_wf_shade<false, false><<<ctx->gridShade[0], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+        case 1: k_wf_shade<false, true><<<ctx->gridShade[1], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+        case 2: k_wf_shade<true, false><<<ctx->gridShade[2], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+        default: k_wf_shade<true, true><<<ctx->gridShade[3], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
       }
       ctx->launches += 2;
       const uint32_t rounds = ctx->nLightSlots;

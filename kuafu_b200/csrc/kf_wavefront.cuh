@@ -29,8 +29,11 @@ namespace kf {
 
 // 7 resident blocks = 72 registers without spills; 8 (64 registers) spills since the hit / miss deal
 // was added and measures 1.6 % slower, 10 (48 registers) 12 % slower.
+#ifndef KF_SHADE_THREADS
+#define KF_SHADE_THREADS 128  // the hit / miss deal works on one block's worth of queue entries
+#endif
 #ifndef KF_SHADE_MIN_BLOCKS
-#define KF_SHADE_MIN_BLOCKS 7
+#define KF_SHADE_MIN_BLOCKS (896 / KF_SHADE_THREADS)
 #endif
 
 // Surface context spilled between light iterations (multi-light scenes only), 6 x float4.
@@ -150,7 +153,7 @@ KF_D void loadCtx(const float4* __restrict__ c, Surface& sf, int& k, V3& acc) {
 
 // ---------------------------------------------------------------------------------------------
 template <bool MULTI, bool DETAIL>
-__global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a, int q, uint32_t depth) {
+__global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a, int q, uint32_t depth) {
   const uint32_t count = a.b.counts[q];
   const uint32_t* __restrict__ queue = a.b.queue[q];
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -165,10 +168,11 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
   // deal whole warps are miss-only and skip it.
   // (two copies of the staging arrays, used in turn: a warp still reading round n is separated from
   // the writers of round n + 2 by the two barriers of round n + 1)
-  __shared__ uint32_t sSlotBuf[2][128];
-  __shared__ uint32_t sQposBuf[2][128];
-  __shared__ int sHitBuf[2][128];
-  __shared__ uint32_t sClassBuf[2][2][4];  // per warp: hits, misses
+  constexpr uint32_t WARPS = KF_SHADE_THREADS / 32;
+  __shared__ uint32_t sSlotBuf[2][KF_SHADE_THREADS];
+  __shared__ uint32_t sQposBuf[2][KF_SHADE_THREADS];
+  __shared__ int sHitBuf[2][KF_SHADE_THREADS];
+  __shared__ uint32_t sClassBuf[2][2][WARPS];  // per warp: hits, misses
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t round = 0;
   // The queue entry and hit record of the NEXT round are fetched while this round is shaded: the deal
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
     uint32_t* sSlot = sSlotBuf[round];
     uint32_t* sQpos = sQposBuf[round];
     int* sHitB = sHitBuf[round];
-    uint32_t(*sClass)[4] = sClassBuf[round];
+    uint32_t(*sClass)[WARPS] = sClassBuf[round];
     bool valid;
     uint32_t slot = 0, qpos = 0;
     int hB = -1;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(128, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a,
       __syncthreads();
       uint32_t hitsBefore = 0, missesBefore = 0, hitsTotal = 0, missesTotal = 0;
 #pragma unroll
-      for (uint32_t w = 0; w < 4; w++) {
+      for (uint32_t w = 0; w < WARPS; w++) {
         const uint32_t h = sClass[0][w], m = sClass[1][w];
         if (w < warp) { hitsBefore += h; missesBefore += m; }
         hitsTotal += h;
