@@ -117,7 +117,8 @@ bool decodePng(const uint8_t* d, size_t n, uint32_t& W, uint32_t& H, std::vector
     }
     pos += 12 + size_t(len);
   }
-  if (!haveHeader || W == 0 || H == 0 || W > kMaxImageSide || H > kMaxImageSide || interlace > 1) return false;
+  if (!haveHeader || W == 0 || H == 0 || W > kMaxImageSide || H > kMaxImageSide || uint64_t(W) * H > (1ull << 28) || interlace > 1)
+    return false;
   int ch;
   switch (colorType) {
     case 0: ch = 1; break;
@@ -228,6 +229,7 @@ bool loadTextureRGBA8(const std::string& path, uint32_t& W, uint32_t& H, std::ve
   std::vector<uint8_t> f;
   if (!readFile(path, f) && !(path[0] != '/' && readFile(global::assetsPath + path, f))) return false;
   if (decodePng(f.data(), f.size(), W, H, rgba)) return true;
+  if (decodeJpeg(f.data(), f.size(), W, H, rgba)) return true;
   return decodePnm(f, W, H, rgba);
 }
 

@@ -301,3 +301,94 @@ def test_reference_projector_pattern_decodes(built):
     want = np.asarray(Image.open(REF_PATTERN).convert("RGBA"))
     assert got.shape == want.shape == (3000, 3000, 4)
     assert np.array_equal(got, want)
+
+
+# ---- JPEG (baseline), written by PIL, decoded by the facade and by PIL ------------------------------------
+def _smooth_image(rng, h, w):
+    """Natural-image-like content (smooth gradients + a few edges): what JPEG is made for, so that two
+    decoders with different IDCT / upsampling arithmetic stay within a few LSB of each other."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.stack([128 + 100 * np.sin(x / 17.0 + k) * np.cos(y / 23.0 - k) for k in range(3)], -1)
+    img[h // 3:h // 2, w // 4:w // 2] += 60
+    img += rng.normal(0, 2, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("subsampling,mode,size,restart", [
+    (0, "RGB", (64, 48), 0),      # 4:4:4
+    (1, "RGB", (67, 45), 0),      # 4:2:2, sizes that are not multiples of the MCU
+    (2, "RGB", (71, 53), 0),      # 4:2:0
+    (2, "RGB", (160, 120), 4),    # restart markers every 4 MCU rows' worth of blocks
+    (0, "L", (50, 37), 0),        # greyscale
+])
+def test_jpeg_reader_against_pil(tmp_path, built, subsampling, mode, size, restart):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(subsampling * 10 + len(mode))
+    w, h = size
+    img = _smooth_image(rng, h, w)
+    pil = Image.fromarray(img if mode == "RGB" else img[..., 0], mode)
+    path = tmp_path / f"t_{mode}_{subsampling}_{restart}.jpg"
+    kw = {"quality": 92}
+    if mode == "RGB":
+        kw["subsampling"] = subsampling
+    if restart:
+        kw["restart_marker_blocks"] = restart
+    try:
+        pil.save(path, "JPEG", **kw)
+    except TypeError:
+        pytest.skip("this PIL cannot write restart markers")
+    got = host.read_texture(path)
+    want = np.asarray(Image.open(path).convert("RGBA"))
+    assert got.shape == want.shape == (h, w, 4) and (got[..., 3] == 255).all()
+    diff = np.abs(got[..., :3].astype(int) - want[..., :3].astype(int))
+    # different IDCT rounding (float vs libjpeg's integer islow) and chroma upsampling filters: a few LSB
+    assert diff.mean() < 1.0 and diff.max() <= (4 if subsampling == 0 else 24), (diff.mean(), diff.max())
+    # and both are close to what was encoded
+    src = img if mode == "RGB" else np.repeat(img[..., :1], 3, -1)
+    assert np.abs(got[..., :3].astype(int) - src.astype(int)).mean() < 4.0
+
+
+def test_progressive_jpeg_is_refused(tmp_path, built):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(1)
+    p = tmp_path / "prog.jpg"
+    Image.fromarray(_smooth_image(rng, 32, 32), "RGB").save(p, "JPEG", progressive=True)
+    with pytest.raises(RuntimeError):
+        host.read_texture(p)
+
+
+@pytest.mark.parametrize("cut", [2, 20, 200, 600, 0.5, 0.9])
+def test_truncated_jpeg_does_not_crash(tmp_path, built, cut):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(2)
+    p = tmp_path / "full.jpg"
+    Image.fromarray(_smooth_image(rng, 64, 64), "RGB").save(p, "JPEG", quality=90)
+    data = p.read_bytes()
+    k = int(len(data) * cut) if isinstance(cut, float) else cut
+    q = tmp_path / "cut.jpg"
+    q.write_bytes(data[:k])
+    try:  # headers cut: refused; entropy data cut: the missing bits read as zero (stb does the same), no crash
+        out = host.read_texture(q)
+        assert out.shape == (64, 64, 4)
+    except RuntimeError:
+        pass
+
+
+def test_corrupted_jpeg_bytes_never_crash(tmp_path, built):
+    """Random byte damage anywhere in a valid file: decoded to something or refused, never a crash (asset
+    files are untrusted input)."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(4)
+    p = tmp_path / "ok.jpg"
+    Image.fromarray(_smooth_image(rng, 48, 64), "RGB").save(p, "JPEG", quality=85, subsampling=2)
+    data = p.read_bytes()
+    q = tmp_path / "damaged.jpg"
+    for _ in range(150):
+        b = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(2, len(b)))] = int(rng.integers(0, 256))
+        q.write_bytes(bytes(b))
+        try:
+            host.read_texture(q)
+        except RuntimeError:
+            pass
