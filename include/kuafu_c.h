@@ -69,7 +69,10 @@ KFC_API int kfcReadKtxCube(const char* path, uint32_t* size, uint8_t* dst, size_
  * restores whole frames. */
 KFC_API int kfcSetSampleShard(KfcRenderer* r, uint32_t begin, uint32_t end, int deferResolve);
 KFC_API int kfcResolve(KfcRenderer* r);
+/* Camera::downloadLatestFrameInto (the frame straight into dst) / Kuafu::downloadLatestFrame (the reference's
+ * by-value signature: a std::vector, then copied into dst). */
 KFC_API int kfcDownloadFrame(KfcRenderer* r, int camera, uint8_t* dst, size_t nbytes);
+KFC_API int kfcDownloadFrameByValue(KfcRenderer* r, int camera, uint8_t* dst, size_t nbytes);
 /* kind: KFRT_AUX_* of kf_rt.h */
 KFC_API int kfcDownloadAux(KfcRenderer* r, int camera, int kind, void* dst, size_t nbytes);
 KFC_API uint32_t kfcClockBase(KfcRenderer* r);

@@ -46,6 +46,7 @@ def load():
     lib.kfcSetSampleShard.argtypes = [vp, u32, u32, i32]
     lib.kfcResolve.argtypes = [vp]
     lib.kfcDownloadFrame.argtypes = [vp, i32, vp, sz]
+    lib.kfcDownloadFrameByValue.argtypes = [vp, i32, vp, sz]
     lib.kfcDownloadAux.argtypes = [vp, i32, i32, vp, sz]
     lib.kfcClockBase.argtypes = [vp]
     lib.kfcClockBase.restype = u32
@@ -214,10 +215,14 @@ class Renderer:
         return dict(zip(("geometries", "materials", "textures", "instances", "cameras", "envSize", "width",
                          "height"), [int(x) for x in out]))
 
-    def download_frame(self, cam=0):
+    def download_frame(self, cam=0, out=None, by_value=False):
+        """Camera::downloadLatestFrameInto a numpy array (`out` to reuse one); by_value: through
+        Kuafu::downloadLatestFrame, the reference's signature (a std::vector, then copied)."""
         c = self.counts()
-        out = np.empty((c["height"], c["width"], 4), "u1")
-        self._ck(self.lib.kfcDownloadFrame(self.h, cam, out.ctypes.data_as(C.c_void_p), out.nbytes), "kfcDownloadFrame")
+        if out is None:
+            out = np.empty((c["height"], c["width"], 4), "u1")
+        fn = self.lib.kfcDownloadFrameByValue if by_value else self.lib.kfcDownloadFrame
+        self._ck(fn(self.h, cam, out.ctypes.data_as(C.c_void_p), out.nbytes), "kfcDownloadFrame")
         return out
 
     def download_aux(self, kind, cam=0):

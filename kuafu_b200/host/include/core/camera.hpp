@@ -70,6 +70,9 @@ class KUAFU_API Camera {
 
   /// width*height*4 bytes, BGRA, sRGB-encoded, alpha 255 (reference camera.cpp:188-207).
   std::vector<uint8_t> downloadLatestFrame();
+  /// Additive: the same bytes straight into the caller's buffer (width*height*4), without the by-value
+  /// vector in between -- for bindings that already own the destination (a numpy array, a ROS message).
+  void downloadLatestFrameInto(uint8_t* dst, size_t nbytes);
   /// Additive outputs the reference lists as TODO (README.md:64-68), all from sample 0 / depth 0.
   std::vector<float> downloadDepth();
   std::vector<int32_t> downloadSegmentation();

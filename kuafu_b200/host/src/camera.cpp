@@ -144,6 +144,18 @@ std::vector<uint8_t> Camera::downloadLatestFrame() {
   return mFrames.stash;
 }
 
+void Camera::downloadLatestFrameInto(uint8_t* dst, size_t nbytes) {
+  KF_ASSERT(mFrames.valid && dst, "Invalid call to Camera::downloadLatestFrameInto");
+  KF_ASSERT(nbytes == size_t(mWidth) * mHeight * 4, "downloadLatestFrameInto: destination size mismatch");
+  if (mFrames.owner && mFrames.serial == mFrames.owner->mSerial) {
+    Context* ctx = mFrames.owner;
+    ctx->check(kfrtDownloadBGRA8(ctx->getDevice(), mFrames.slot, dst, nbytes), "kfrtDownloadBGRA8");
+    return;
+  }
+  KF_ASSERT(mFrames.stash.size() == nbytes, "Invalid call to Camera::downloadLatestFrameInto");
+  std::memcpy(dst, mFrames.stash.data(), nbytes);
+}
+
 template <typename T>
 static std::vector<T> reinterpretBytes(const std::vector<uint8_t>& b) {
   std::vector<T> out(b.size() / sizeof(T));

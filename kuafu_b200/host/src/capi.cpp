@@ -156,8 +156,16 @@ int kfcResolve(KfcRenderer* r) {
 
 int kfcDownloadFrame(KfcRenderer* r, int camera, uint8_t* dst, size_t nbytes) {
   return guarded([&] {
+    // the caller owns the destination: Camera::downloadLatestFrameInto (the by-value downloadLatestFrame of the
+    // reference's signature is kfcDownloadFrameByValue)
+    r->cameras.at(size_t(camera))->downloadLatestFrameInto(dst, nbytes);
+  });
+}
+
+int kfcDownloadFrameByValue(KfcRenderer* r, int camera, uint8_t* dst, size_t nbytes) {
+  return guarded([&] {
     const std::vector<uint8_t> f = r->renderer->downloadLatestFrame(r->cameras.at(size_t(camera)));
-    if (f.size() != nbytes) throw std::runtime_error("kfcDownloadFrame: destination size mismatch");
+    if (f.size() != nbytes) throw std::runtime_error("kfcDownloadFrameByValue: destination size mismatch");
     std::memcpy(dst, f.data(), nbytes);
   });
 }

@@ -208,3 +208,23 @@ def test_small_batches_equal_one_batch(rt, orc_mod, monkeypatch):
     ctx2.render(cams, sc.w, sc.h, sc.pc, clock_base=2)
     assert np.array_equal(ctx2.download_aux(wire.AUX_SUM32F).view(np.uint32), one.view(np.uint32))
     ctx2.close()
+
+
+def test_frame_into_a_caller_buffer_equals_the_by_value_frame(built):
+    """Camera::downloadLatestFrameInto (additive) and Kuafu::downloadLatestFrame (the reference's by-value
+    signature) hand out the same bytes, also for a frame that was displaced by a later render (stash)."""
+    from kuafu_b200 import host
+    r = host.Renderer(device=0, accumulate=False)
+    r.load_scene("active", 96, 54, 1)
+    r.set_camera(0)
+    r.run()
+    a_into = r.download_frame(0).copy()
+    a_val = r.download_frame(0, by_value=True).copy()
+    assert np.array_equal(a_into, a_val) and int(a_into[..., 3].min()) == 255
+    r.set_camera(1)
+    r.run()  # camera 0's frame now lives in its stash
+    assert np.array_equal(r.download_frame(0), a_into)
+    assert np.array_equal(r.download_frame(0, by_value=True), a_into)
+    reuse = np.zeros_like(a_into)
+    assert r.download_frame(1, out=reuse) is reuse and not np.array_equal(reuse, a_into)
+    r.close()
