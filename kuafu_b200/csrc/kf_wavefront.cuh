@@ -242,9 +242,18 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
     if (valid) {
       const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[qpos];
       const float4 sw = a.b.stateW[slot];
-      float4 sc4 = a.b.stateC[slot];
-      V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
+      V3 weight = mk3(sw.x, sw.y, sw.z);
       uint32_t seed = __float_as_uint(sw.w);
+      // The path's colour is touched only when something is added to it: a miss, an emissive surface, or
+      // -- to keep the reference's `color += emission * weight` with emission = 0 exact -- a weight that
+      // is no longer finite (0 * Inf = NaN).  Every other hit leaves its 16 bytes where they are: 32 of
+      // the 176 bytes a hit moved through this stage.
+      auto addColor = [&](V3 term) {
+        const float4 sc4 = a.b.stateC[slot];
+        const V3 color = mk3(sc4.x, sc4.y, sc4.z) + term;
+        a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+      };
+      auto finite3 = [](V3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); };
       const V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
       uint32_t tex = 0;
       const uint32_t s = slot / a.slotsPerSample;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
       }
       if (hB == -1) {
         const V3 emission = shadeMiss(a.sc, a.pc, rd, tex);
-        color += emission * weight;
+        addColor(emission * weight);
         if (firstHitOutputs) {
           a.albedo[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
           a.normal[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -265,7 +274,6 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           a.hitT[pi] = 0.0f;
           a.depth[pi] = 0.0f;
         }
-        a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
       } else {
         isHit = true;
         Hit hit;
@@ -286,18 +294,17 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
         Surface sf;
         V3 L, w, albedo, emission;
         if (!shadeSurface(a.sc, hit, ro, rd, seed, sf, L, w, albedo, emission, tex)) {
-          color += emission * weight;  // emissive surface ends the path (rchit:330-334)
+          addColor(emission * weight);  // emissive surface ends the path (rchit:330-334)
           if (firstHitOutputs) {
             a.albedo[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
             a.normal[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
           }
-          a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
         } else {
           if (firstHitOutputs) {
             a.albedo[pi] = make_float4(albedo.x, albedo.y, albedo.z, 1.f);
             a.normal[pi] = make_float4(sf.N.x, sf.N.y, sf.N.z, 1.f);
           }
-          color += mk3(0.0f) * weight;  // ray.emission = 0 (rgen:109 keeps NaN/Inf semantics)
+          if (!finite3(weight)) addColor(mk3(0.0f) * weight);  // ray.emission = 0 (rgen:109 keeps NaN/Inf semantics)
           weight *= w;                  // rgen:110; the NEE sum is scaled by the post-BSDF weight
           // next extension ray (rchit:462-463); the occlusion rays share its origin
           a.b.rayO[slot] = make_float4(sf.worldPos.x, sf.worldPos.y, sf.worldPos.z, 0.0f);
@@ -312,14 +319,12 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
             a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
             if (MULTI) storeCtx(a.b.ctx + size_t(6) * slot, sf, k, mk3(0.0f));
             a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
-            a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
             toShadow = true;
           } else {
             // no light needs a ray: shadow_color = 0, advance right away
-            color += mk3(0.0f) * weight;
+            if (!finite3(weight)) addColor(mk3(0.0f) * weight);
             toNext = advancePath(a.pc, depth, weight, seed);
             a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
-            a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
           }
         }
       }
@@ -362,11 +367,13 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
       nextOcc = a.b.hitB[i + stride];
     }
     if (valid) {
-      const float4 sw = a.b.stateW[slot], sc4 = a.b.stateC[slot], spec = a.b.shadowC[slot];
-      V3 weight = mk3(sw.x, sw.y, sw.z), color = mk3(sc4.x, sc4.y, sc4.z);
+      const float4 sw = a.b.stateW[slot];
+      V3 weight = mk3(sw.x, sw.y, sw.z);
       uint32_t seed = __float_as_uint(sw.w);
       V3 shadowColor = mk3(0.0f);
       if (!occluded) {
+        // an occluded light leaves no trace: its speculative contribution is never read
+        const float4 spec = a.b.shadowC[slot];
         shadowColor = mk3(spec.x, spec.y, spec.z);
         seed = __float_as_uint(spec.w);
       }
@@ -397,10 +404,15 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
         shadowColor = acc;
       }
       if (!pending) {
-        color += shadowColor * weight;  // rgen:111
+        // rgen:111; a zero shadow colour under a finite weight adds nothing, and the path's colour stays
+        // where it is (0 * Inf = NaN still lands, as in the reference)
+        if (anyNe(shadowColor, mk3(0.0f)) || !(isfinite(weight.x) && isfinite(weight.y) && isfinite(weight.z))) {
+          const float4 sc4 = a.b.stateC[slot];
+          const V3 color = mk3(sc4.x, sc4.y, sc4.z) + shadowColor * weight;
+          a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+        }
         toNext = advancePath(a.pc, depth, weight, seed);
         a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
-        a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
       }
     }
     queueAppend(a.b.queue[qNext], a.b.counts + qNext, toNext, slot);
