@@ -240,7 +240,13 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
     }
     bool toNext = false, toShadow = false, isHit = false;
     if (valid) {
-      const float4 o4 = a.b.rayO[slot], d4 = a.b.rayD[slot], hA = a.b.hitA[qpos];
+      // a miss needs neither the ray's origin nor a hit record
+      const float4 d4 = a.b.rayD[slot];
+      float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), hA = o4;
+      if (hB != -1) {
+        o4 = a.b.rayO[slot];
+        hA = a.b.hitA[qpos];
+      }
       const float4 sw = a.b.stateW[slot];
       V3 weight = mk3(sw.x, sw.y, sw.z);
       uint32_t seed = __float_as_uint(sw.w);
@@ -412,7 +418,9 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
           a.b.stateC[slot] = make_float4(color.x, color.y, color.z, 0.0f);
         }
         toNext = advancePath(a.pc, depth, weight, seed);
-        a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
+        // (an occluded light below the Russian-roulette depth leaves weight and seed as they were)
+        if (seed != __float_as_uint(sw.w) || anyNe(weight, mk3(sw.x, sw.y, sw.z)))
+          a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
       }
     }
     queueAppend(a.b.queue[qNext], a.b.counts + qNext, toNext, slot);
