@@ -681,6 +681,7 @@ def main():
             "per_gpu_mrays": value / world,
             "rays_per_step": rays_total / args.steps,
             "first_frame_ms": first_frame_ms, "frame_check": frame_check,
+            "traversal_structure": "instance subtrees" if int(stats["subtreeNodeCount"]) else "two-level",
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t / args.steps * 1e3,

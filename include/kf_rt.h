@@ -157,6 +157,10 @@ typedef struct KfrtBvhStats {
   uint32_t triangleBytes;      /* bytes per stored triangle */
   uint32_t instanceBytes;      /* bytes per instance record read on TLAS leaf entry */
   uint32_t tlasRebuilds;       /* kfrtRefitTlas calls that rebuilt the top level instead (quality watch) */
+  uint64_t subtreeNodeCount;   /* wide nodes of top level + world-space instance subtrees (kfrtSetInstanceSubtrees); 0 while the two-level structure is walked (as of the last kfrtRender) */
+  uint64_t subtreeTriangles;   /* triangle records in them (== instancedTriangles of the visible instances) */
+  uint32_t subtreeDepth;       /* levels: top level + deepest subtree */
+  uint32_t subtreeBuilds;      /* times they have been built in this context */
 } KfrtBvhStats;
 
 typedef struct KfrtContext KfrtContext;
@@ -239,6 +243,18 @@ KFRT_API int kfrtBuildTlas(KfrtContext* ctx);
  * the quality of the refitted tree (area sum of its nodes, read back one call late) and runs the full
  * build instead when it has degraded past 1.1x its value at build time. */
 KFRT_API int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n);
+/* World-space instance subtrees (no counterpart in the reference, which leaves instancing to the driver
+ * behind vkCmdBuildAccelerationStructuresKHR, reference src/core/rt/rt.cpp:116-140): when the instanced
+ * triangles of the scene number at most maxTriangles (and its visible instances at most 1 024), every
+ * instance can get its own subtree in world space under the top level, and kfrtRender then walks that
+ * single-space hierarchy instead of the two-level structure -- same hit buffers bit for bit, see kf_wsi.cuh.
+ * mode 0: never.  mode 1 (default): scenes that have not been refitted since kfrtBuildTlas; the first
+ * kfrtRender after the build times one sample of its frame with either structure and keeps the faster
+ * (KfrtBvhStats.subtreeNodeCount != 0 afterwards: the subtrees won).  mode 2: whenever the scene fits,
+ * rebuilt by the first kfrtRender after every kfrtBuildTlas / kfrtRefitTlas.  maxTriangles 0 keeps the
+ * current budget (default 4 Mi).  Environment overrides at kfrtCreate: KFRT_INSTANCE_SUBTREES,
+ * KFRT_INSTANCE_SUBTREES_MAX_TRIS. */
+KFRT_API int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTriangles);
 KFRT_API int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out);
 
 /* ------------------------------------------------------------------------------------------------

@@ -247,6 +247,8 @@ struct TexRec {
 
 struct SceneDev {
   const Node8* tlasNodes;  // top level: Node8 and InstNode records in one array (kf_bvh_build.cuh)
+  const Node8* wsiNodes;   // top level + world-space instance subtrees in one array (kf_wsi.cuh); the traversal
+  const Tri48* wsiTris;    // stages walk it instead of the two-level structure while it is valid
   const InstRec* inst;
   const KfrtInstance* instSsbo;
   const GeomRec* geoms;

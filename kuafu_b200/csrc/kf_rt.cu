@@ -18,6 +18,7 @@
 #include "kf_shade.cuh"
 #include "kf_traverse.cuh"
 #include "kf_wavefront.cuh"
+#include "kf_wsi.cuh"
 
 using namespace kf;
 
@@ -191,6 +192,23 @@ struct KfrtContext {
   uint32_t tlasBlasDepth = 0;  // deepest bottom level among the instances of the last build
   bool tlasSahOptIn = false;   // k_tlas_sah may use its large dynamic shared memory on this device
   uint64_t tlasRebuilds = 0;
+
+  // world-space instance subtrees (kf_wsi.cuh): built lazily by the first kfrtRender after the instance
+  // set or a transform has changed, when the instanced triangles fit the budget
+  int wsiMode = 1;  // 0 never; 1 static scenes within the budget, if a timed probe says they are faster; 2 whenever they fit
+  uint64_t wsiMaxTris = uint64_t(4) << 20;
+  bool wsiValid = false, wsiDirty = true;
+  bool wsiMoving = false;  // kfrtRefitTlas since the last kfrtBuildTlas: mode 1 leaves such scenes on the two-level walk
+  int wsiChoice = 0;       // mode 1: 0 not probed yet, 1 the two-level structure won, 2 the instance subtrees won
+  float wsiProbeMs[2] = {0.0f, 0.0f};  // what the probe measured: two-level, instance subtrees
+  DevBuf<Node8> wsiNodes;
+  DevBuf<Tri48> wsiTris;
+  DevBuf<KfrtVertex> wsiVerts;
+  DevBuf<WsiInst> wsiVis;
+  DevBuf<uint32_t> wsiRank;
+  uint64_t wsiNodeCount = 0, wsiTriCount = 0, wsiBuilds = 0;
+  uint32_t wsiDepth = 0;
+  int gridTraceWsi[4] = {0, 0, 0, 0};
 
   // outputs
   uint32_t nCams = 0, width = 0, height = 0;
@@ -687,6 +705,11 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
     }
   }
   if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KFRT_INSTANCE_SUBTREES")) ctx->wsiMode = std::max(0, std::min(2, std::atoi(e)));
+  if (const char* e = std::getenv("KFRT_INSTANCE_SUBTREES_MAX_TRIS")) {
+    const long long v = std::atoll(e);
+    if (v > 0) ctx->wsiMaxTris = uint64_t(v);
+  }
   if (const char* e = std::getenv("KFRT_BATCH_SLOTS")) {
     const long long v = std::atoll(e);
     if (v > 0) ctx->batchSlotTarget = size_t(v);
@@ -729,6 +752,7 @@ int kfrtDestroy(KfrtContext* ctx) {
   ctx->env.release(); ctx->dl.release(); ctx->pl.release(); ctx->al.release(); ctx->alProjView.release();
   ctx->srgbToLinear.release(); ctx->srgbThreshold.release(); ctx->instDev.release();
   ctx->instRec.release(); ctx->instBoxInt.release(); ctx->tlasNodes.release(); ctx->tlasArea.release();
+  ctx->wsiNodes.release(); ctx->wsiTris.release(); ctx->wsiVerts.release(); ctx->wsiVis.release(); ctx->wsiRank.release();
   if (ctx->tlasRb) cudaFreeHost(ctx->tlasRb);
   if (ctx->tlasAreaReady) cudaEventDestroy(ctx->tlasAreaReady);
   if (ctx->tlasBuildReady) cudaEventDestroy(ctx->tlasBuildReady);
@@ -1033,6 +1057,8 @@ static int buildTopLevel(KfrtContext* ctx, bool wait) {
   if (rc) return rc;
   ctx->tlasBuildPending = ctx->tlasAreaPending = false;
   ctx->tlasAreaAtBuild = 0.0f;
+  ctx->wsiValid = false;  // the instance subtrees are rebuilt by the next kfrtRender (buildWsi)
+  ctx->wsiDirty = true;
   if (n == 0) {
     ctx->nTlasNodes = 0;
     ctx->tlasBuilt = true;
@@ -1111,6 +1137,177 @@ static int buildTopLevel(KfrtContext* ctx, bool wait) {
   return KFRT_OK;
 }
 
+// World-space instance subtrees (kf_wsi.cuh) from the current instances, transforms and top level: the
+// vertices of every visible instance in world space, the batched bottom-level builder over them (one
+// pseudo-geometry per instance), then the assembly -- top-level nodes, subtree roots in the instance
+// slots, the other subtree nodes behind, object-space triangle records in leaf order.  One stream
+// synchronisation (the collapse reports its node counts), as in buildBlasBatch.
+static int buildWsi(KfrtContext* ctx) {
+  ctx->wsiValid = false;
+  ctx->wsiDirty = false;
+  if (ctx->wsiMode == 0 || ctx->instHost.empty()) return KFRT_OK;
+  if (ctx->wsiMode == 1 && (ctx->wsiMoving || ctx->wsiChoice == 1)) return KFRT_OK;
+  const uint32_t nInst = uint32_t(ctx->instHost.size());
+  std::vector<WsiInst> vis;
+  std::vector<uint32_t> rank(nInst, 0xffffffffu);
+  std::vector<BatchGeom> table;
+  uint64_t nTris64 = 0, nVerts64 = 0;
+  for (uint32_t i = 0; i < nInst; i++) {
+    const uint32_t gi = ctx->instHost[i].geometryIndex;
+    if (gi >= ctx->geoms.size()) return KFRT_OK;
+    const GeomHost& g = ctx->geoms[gi];
+    if (!g.present || !g.nodes || g.nIdx / 3 == 0) continue;
+    nTris64 += g.nIdx / 3;
+    nVerts64 += g.nVerts;
+    if (vis.size() >= KF_BATCH_MAX_GEOMS || nTris64 > ctx->wsiMaxTris || nVerts64 >= (uint64_t(1) << 31)) return KFRT_OK;
+    WsiInst v{};
+    v.instance = i;
+    v.vertOffset = uint32_t(nVerts64 - g.nVerts);
+    v.flags = g.opaque ? 0u : 2u;
+    rank[i] = uint32_t(vis.size());
+    vis.push_back(v);
+  }
+  if (vis.empty()) return KFRT_OK;
+  if (ctx->tlasBuildPending) {  // the top level's node count is needed below
+    KF_CUDA(ctx, cudaEventSynchronize(ctx->tlasBuildReady));
+    int rc = consumeTlasBuild(ctx);
+    if (rc) return rc;
+  }
+  const uint32_t count = uint32_t(vis.size());
+  const uint32_t n = uint32_t(nTris64);
+  BuildState& st = ctx->blasBuild;
+  cudaStream_t stream = ctx->stream;
+  KF_CUDA(ctx, ctx->wsiVerts.ensure(size_t(nVerts64)));
+  KF_CUDA(ctx, ctx->wsiVis.ensure(count));
+  KF_CUDA(ctx, ctx->wsiRank.ensure(nInst));
+  table.resize(count);
+  uint32_t triAt = 0, nodeSlots = 0, maxTris = 0, maxVerts = 1;
+  for (uint32_t k = 0; k < count; k++) {
+    const GeomHost& g = ctx->geoms[ctx->instHost[vis[k].instance].geometryIndex];
+    BatchGeom& b = table[k];
+    b.verts = ctx->wsiVerts.p + vis[k].vertOffset;
+    b.idx = g.idx;
+    b.matIndex = g.matIndex;
+    b.nVerts = g.nVerts;
+    b.nTris = g.nIdx / 3;
+    b.triOffset = triAt;
+    b.nodeOffset = nodeSlots;
+    b.nodesAlloc = nullptr;
+    b.tris = nullptr;
+    b.shade = nullptr;
+    triAt += b.nTris;
+    nodeSlots += b.nTris + 1;
+    maxTris = std::max(maxTris, b.nTris);
+    maxVerts = std::max(maxVerts, b.nVerts);
+  }
+  KF_CUDA(ctx, st.batchGeoms.ensure(count));
+  KF_CUDA(ctx, st.batchCounters.ensure(size_t(KF_BATCH_COUNTERS) * count));
+  KF_CUDA(ctx, st.batchBoxes.ensure(size_t(6) * count));
+  KF_CUDA(ctx, st.primGeom.ensure(n));
+  KF_CUDA(ctx, st.primBox.ensure(size_t(6) * n));
+  KF_CUDA(ctx, st.hist.ensure(size_t(256) * gridFor(n, KF_SORT_TILE)));
+  KF_CUDA(ctx, st.keysA.ensure(n));
+  KF_CUDA(ctx, st.keysB.ensure(n));
+  KF_CUDA(ctx, st.valsA.ensure(n));
+  KF_CUDA(ctx, st.valsB.ensure(n));
+  KF_CUDA(ctx, st.children.ensure(n));
+  KF_CUDA(ctx, st.range.ensure(n));
+  KF_CUDA(ctx, st.parent.ensure(size_t(2) * n));
+  KF_CUDA(ctx, st.flags.ensure(n));
+  KF_CUDA(ctx, st.nodeBox.ensure(size_t(6) * n));
+  KF_CUDA(ctx, st.outNodes.ensure(nodeSlots));
+  KF_CUDA(ctx, st.wideBinary.ensure(nodeSlots));
+  KF_CUDA(ctx, st.outPrim.ensure(n));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->wsiVis.p, vis.data(), sizeof(WsiInst) * count, cudaMemcpyHostToDevice, stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->wsiRank.p, rank.data(), sizeof(uint32_t) * nInst, cudaMemcpyHostToDevice, stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.batchGeoms.p, table.data(), sizeof(BatchGeom) * count, cudaMemcpyHostToDevice, stream));
+  const unsigned vx = std::max(1u, std::min<unsigned>(gridFor(maxVerts, 256), std::max(1u, unsigned(ctx->numSMs) * 8u / count)));
+  k_wsi_world_verts<<<dim3(vx, count), 256, 0, stream>>>(ctx->wsiVis.p, ctx->instDev.p, ctx->blasInfo.p, ctx->wsiVerts.p);
+  k_batch_init<<<gridFor(6 * size_t(count), 256), 256, 0, stream>>>(st.batchBoxes.p, count);
+  k_batch_tri_boxes<<<gridFor(n, 256), 256, 0, stream>>>(st.batchGeoms.p, count, n, st.primBox.p, st.primGeom.p, st.batchBoxes.p);
+  if (n > 1) {
+    k_batch_morton<<<gridFor(n, 256), 256, 0, stream>>>(st.primBox.p, st.primGeom.p, n, st.batchBoxes.p, st.keysA.p, st.valsA.p);
+    int geomBits = 0;
+    while ((1u << geomBits) < count) geomBits++;
+    int rc = radixSort(ctx, st, n, 3 * KF_BATCH_MORTON_BITS + geomBits);
+    if (rc) return rc;
+    k_lbvh_hierarchy<<<gridFor(n - 1, 256), 256, 0, stream>>>(st.sortedKeys, int(n), st.children.p, st.range.p, st.parent.p);
+    KF_CUDA(ctx, cudaMemsetAsync(st.flags.p, 0, sizeof(uint32_t) * n, stream));
+    k_lbvh_bounds<<<gridFor(n, 256), 256, 0, stream>>>(int(n), st.children.p, st.parent.p, st.primBox.p, st.sortedVals,
+                                                       st.nodeBox.p, st.flags.p);
+  } else {
+    const uint32_t zero = 0;
+    KF_CUDA(ctx, cudaMemcpyAsync(st.valsA.p, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+    st.sortedVals = st.valsA.p;
+  }
+  k_batch_roots<<<gridFor(count, 128), 128, 0, stream>>>(st.batchGeoms.p, count, st.range.p, n, st.batchCounters.p, st.wideBinary.p);
+  BatchCollapseArgs ca;
+  ca.geoms = st.batchGeoms.p;
+  ca.nGeoms = count;
+  ca.base.n = int(n);
+  ca.base.children = st.children.p;
+  ca.base.range = st.range.p;
+  ca.base.nodeBox = st.nodeBox.p;
+  ca.base.primBox = st.primBox.p;
+  ca.base.vals = st.sortedVals;
+  ca.base.outNodes = st.outNodes.p;
+  ca.base.outPrim = st.outPrim.p;
+  ca.base.wideBinary = st.wideBinary.p;
+  ca.base.wideMembers = nullptr;
+  ca.base.counters = st.batchCounters.p;
+  ca.base.slotOfInst = nullptr;
+  const unsigned bx = std::max(1u, std::min<unsigned>(gridFor(maxTris / 4 + 1, 64), std::max(1u, unsigned(ctx->numSMs) * 16u / count)));
+  std::vector<uint32_t> counters(size_t(KF_BATCH_COUNTERS) * count);
+  int levels = 4;
+  for (uint32_t m = maxTris; m > 16; m >>= 3) levels++;
+  for (bool done = false; !done;) {
+    for (int level = 0; level < levels; level++) {
+      k_batch_collapse_level<<<dim3(bx, count), 64, 0, stream>>>(ca);
+      k_batch_next_level<<<gridFor(count, 128), 128, 0, stream>>>(st.batchCounters.p, count);
+    }
+    KF_CUDA(ctx, cudaMemcpyAsync(counters.data(), st.batchCounters.p, sizeof(uint32_t) * counters.size(), cudaMemcpyDeviceToHost, stream));
+    KF_CUDA(ctx, cudaStreamSynchronize(stream));
+    done = true;
+    for (uint32_t k = 0; k < count; k++) {
+      const uint32_t* c = &counters[size_t(KF_BATCH_COUNTERS) * k];
+      if (c[0] > table[k].nTris + 1) KF_FAIL(ctx, KFRT_ERR_CUDA, "internal: wide node count exceeded its bound");
+      if (c[2] < c[3]) done = false;
+    }
+    levels = 4;
+  }
+  // assembly: [top level incl. the instance slots][nodes 1.. of every subtree]
+  const uint32_t nTop = ctx->tlasBuild.nWide;
+  uint64_t nodeAt = nTop;
+  uint32_t depth = 0;
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t nWide = counters[size_t(KF_BATCH_COUNTERS) * k];
+    vis[k].nodeStart = uint32_t(nodeAt);
+    nodeAt += nWide - 1;
+    depth = std::max(depth, counters[size_t(KF_BATCH_COUNTERS) * k + 4]);
+  }
+  if (nodeAt >= (uint64_t(1) << 32)) return KFRT_OK;
+  if (ctx->tlasBuild.depth + depth > uint32_t(KF_STACK_SHARED + KF_STACK))
+    KF_FAIL(ctx, KFRT_ERR_LIMIT, "acceleration structure deeper than the traversal stack (KF_STACK)");
+  KF_CUDA(ctx, ctx->wsiNodes.ensure(size_t(nodeAt)));
+  KF_CUDA(ctx, ctx->wsiTris.ensure(n));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->wsiVis.p, vis.data(), sizeof(WsiInst) * count, cudaMemcpyHostToDevice, stream));
+  KF_CUDA(ctx, cudaMemcpyAsync(ctx->wsiNodes.p, ctx->tlasNodes.p, sizeof(Node8) * nTop, cudaMemcpyDeviceToDevice, stream));
+  k_wsi_empty_slots<<<gridFor(nInst, 128), 128, 0, stream>>>(ctx->wsiRank.p, nInst, ctx->tlasBuild.slotOfInst.p, ctx->wsiNodes.p);
+  k_wsi_place_nodes<<<dim3(bx, count), 128, 0, stream>>>(ctx->wsiVis.p, st.batchGeoms.p, st.batchCounters.p, st.outNodes.p,
+                                                         ctx->tlasBuild.slotOfInst.p, ctx->wsiNodes.p);
+  k_wsi_write_tris<<<gridFor(n, 256), 256, 0, stream>>>(ctx->wsiVis.p, st.batchGeoms.p, ctx->instDev.p, ctx->blasInfo.p,
+                                                        st.primGeom.p, st.outPrim.p, n, ctx->wsiTris.p);
+  KF_CUDA(ctx, cudaGetLastError());
+  // the tables on the host go out of scope: the copies above must have read them
+  KF_CUDA(ctx, cudaStreamSynchronize(stream));
+  ctx->wsiNodeCount = nodeAt;
+  ctx->wsiTriCount = n;
+  ctx->wsiDepth = ctx->tlasBuild.depth + depth;
+  ctx->wsiBuilds++;
+  ctx->wsiValid = true;
+  return KFRT_OK;
+}
+
 int kfrtBuildTlas(KfrtContext* ctx) {
   KF_CHECK_CTX(ctx);
   if (!ctx->blasBuilt) KF_FAIL(ctx, KFRT_ERR_NOT_BUILT, "kfrtBuildTlas before kfrtBuildBlas");
@@ -1120,6 +1317,8 @@ int kfrtBuildTlas(KfrtContext* ctx) {
     int rc = uploadTables(ctx);
     if (rc) return rc;
   }
+  ctx->wsiMoving = false;
+  ctx->wsiChoice = 0;
   return buildTopLevel(ctx, true);
 }
 
@@ -1130,6 +1329,9 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   if (n == 0) return KFRT_OK;
   if (!transforms) KF_FAIL(ctx, KFRT_ERR_INVALID, "null transforms");
   for (uint32_t i = 0; i < n; i++) std::memcpy(ctx->instHost[i].transform, transforms + 16 * i, 64);
+  ctx->wsiValid = false;
+  ctx->wsiDirty = true;
+  ctx->wsiMoving = true;
   // A refit keeps the hierarchy of the last build; when the instances have moved far from where they
   // were then, its boxes overlap and every ray pays (articulated scene: 6.3 top-level node visits per
   // ray after a build, 38 after 40 frames of refits).  The area sum of the last refit (read back
@@ -1174,6 +1376,17 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   return KFRT_OK;
 }
 
+int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTriangles) {
+  KF_CHECK_CTX(ctx);
+  if (mode < 0 || mode > 2) KF_FAIL(ctx, KFRT_ERR_INVALID, "instance-subtree mode must be 0, 1 or 2");
+  ctx->wsiMode = mode;
+  ctx->wsiChoice = 0;
+  if (maxTriangles) ctx->wsiMaxTris = maxTriangles;
+  ctx->wsiValid = false;
+  ctx->wsiDirty = true;
+  return KFRT_OK;
+}
+
 int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   KF_CHECK_CTX(ctx);
   if (!out) KF_FAIL(ctx, KFRT_ERR_INVALID, "null stats");
@@ -1195,8 +1408,12 @@ int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out) {
   out->tlasNodeCount = ctx->nTlasNodes;
   out->nodeBytes = sizeof(Node8);
   out->triangleBytes = sizeof(Tri48);
-  out->instanceBytes = sizeof(InstNode);
+  out->instanceBytes = ctx->wsiValid ? 48u : uint32_t(sizeof(InstNode));  // subtrees: the three rows of the inverse, per change of instance
   out->tlasRebuilds = uint32_t(ctx->tlasRebuilds);
+  out->subtreeNodeCount = ctx->wsiValid ? ctx->wsiNodeCount : 0;
+  out->subtreeTriangles = ctx->wsiValid ? ctx->wsiTriCount : 0;
+  out->subtreeDepth = ctx->wsiValid ? ctx->wsiDepth : 0;
+  out->subtreeBuilds = uint32_t(ctx->wsiBuilds);
   return KFRT_OK;
 }
 
@@ -1218,6 +1435,15 @@ static int persistentGrid(KfrtContext* ctx, K kernel, int blockSize) {
 // One traversal stage launch: closest hit (any == false) or occlusion.
 static void launchTrace(KfrtContext* ctx, const TraceArgs& te, bool any, bool detail) {
   const int v = (any ? 2 : 0) + (detail ? 1 : 0);
+  if (te.sc.wsiNodes) {
+    switch (v) {
+      case 0: k_wf_trace_wsi<false, false><<<ctx->gridTraceWsi[0], 128, 0, ctx->stream>>>(te); break;
+      case 1: k_wf_trace_wsi<false, true><<<ctx->gridTraceWsi[1], 128, 0, ctx->stream>>>(te); break;
+      case 2: k_wf_trace_wsi<true, false><<<ctx->gridTraceWsi[2], 128, 0, ctx->stream>>>(te); break;
+      default: k_wf_trace_wsi<true, true><<<ctx->gridTraceWsi[3], 128, 0, ctx->stream>>>(te); break;
+    }
+    return;
+  }
   switch (v) {
     case 0: k_wf_trace<false, false><<<ctx->gridTrace[0], 128, 0, ctx->stream>>>(te); break;
     case 1: k_wf_trace<false, true><<<ctx->gridTrace[1], 128, 0, ctx->stream>>>(te); break;
@@ -1259,6 +1485,10 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     ctx->gridTrace[1] = persistentGrid(ctx, k_wf_trace<false, true>, 128);
     ctx->gridTrace[2] = persistentGrid(ctx, k_wf_trace<true, false>, 128);
     ctx->gridTrace[3] = persistentGrid(ctx, k_wf_trace<true, true>, 128);
+    ctx->gridTraceWsi[0] = persistentGrid(ctx, k_wf_trace_wsi<false, false>, 128);
+    ctx->gridTraceWsi[1] = persistentGrid(ctx, k_wf_trace_wsi<false, true>, 128);
+    ctx->gridTraceWsi[2] = persistentGrid(ctx, k_wf_trace_wsi<true, false>, 128);
+    ctx->gridTraceWsi[3] = persistentGrid(ctx, k_wf_trace_wsi<true, true>, 128);
     ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, KF_SHADE_THREADS);
     ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, KF_SHADE_THREADS);
     ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, KF_SHADE_THREADS);
@@ -1401,6 +1631,56 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
 
 extern "C" {
 
+// Mode 1 of kfrtSetInstanceSubtrees: which structure is faster depends on the scene AND on how many rays
+// a launch carries (instance subtrees save the instance phase and a few dependent fetches per ray; the
+// two-level walk has the exact per-instance culls, fewer node steps and the smaller working set --
+// measured on the BASELINE configs at full size: config 2 -15 % and config 1 -5 % of the closest-hit stage
+// with subtrees, config 3 +4 %, config 4 +10 %; yet a ONE-sample frame of config 4 is 6 % faster with
+// subtrees, because small launches are bound by latency, not by throughput).  So the first kfrtRender after
+// a build renders a batch of the frame it was asked for -- up to 32 Mi path slots of it, the size at
+// which the ratio has settled -- once with each structure, and keeps the faster; the subtrees must win by
+// 2 %.  Both give the same buffers bit for bit, and the frame proper overwrites what the probes wrote.
+#define KF_PROBE_SLOTS (size_t(32) << 20)
+static int probeStructures(KfrtContext* ctx, const RenderArgs& full) {
+  RenderArgs p = full;
+  const size_t slotsPerSample = size_t(full.nCams) * ((full.w + 7) / 8) * ((full.h + 3) / 4) * 32;
+  const uint32_t samples = uint32_t(std::max<size_t>(1, KF_PROBE_SLOTS / slotsPerSample));
+  p.s1 = std::min(full.s1, p.s0 + samples);
+  const bool timers = ctx->stageTimers, log = ctx->traceLog;
+  ctx->stageTimers = false;
+  ctx->traceLog = false;  // (its per-launch synchronisation would be what the probe measures)
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  KF_CUDA(ctx, cudaEventCreate(&ev[0]));
+  KF_CUDA(ctx, cudaEventCreate(&ev[1]));
+  float ms[2] = {3.0e38f, 3.0e38f};
+  int rc = KFRT_OK;
+  for (int which = 1; which >= 0 && rc == KFRT_OK; which--) {  // (the first one also pays the path-state allocation)
+    for (int pass = 0; pass < (which == 1 ? 2 : 1) && rc == KFRT_OK; pass++) {
+      p.sc.wsiNodes = which ? ctx->wsiNodes.p : nullptr;
+      p.sc.wsiTris = which ? ctx->wsiTris.p : nullptr;
+      cudaEventRecord(ev[0], ctx->stream);
+      rc = renderWavefront(ctx, p);
+      cudaEventRecord(ev[1], ctx->stream);
+      if (rc == KFRT_OK && cudaEventSynchronize(ev[1]) == cudaSuccess) cudaEventElapsedTime(&ms[which], ev[0], ev[1]);
+    }
+  }
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  ctx->stageTimers = timers;
+  ctx->traceLog = log;
+  ctx->stageUsed = 0;
+  if (rc) return rc;
+  ctx->wsiProbeMs[0] = ms[0];
+  ctx->wsiProbeMs[1] = ms[1];
+  ctx->wsiChoice = ms[1] < 0.98f * ms[0] ? 2 : 1;
+  if (ctx->traceLog)
+    std::fprintf(stderr, "[kfrt] structure probe (%u samples): two-level %.3f ms, instance subtrees %.3f ms -> %s\n",
+                 p.s1 - p.s0, ms[0], ms[1], ctx->wsiChoice == 2 ? "instance subtrees" : "two-level");
+  if (ctx->wsiChoice == 1) ctx->wsiValid = false;  // (its storage stays for the next build)
+  KF_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * 16, ctx->stream));
+  return KFRT_OK;
+}
+
 static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t h) {
   const size_t np = size_t(nCams) * w * h;
   const bool changed = nCams != ctx->nCams || w != ctx->width || h != ctx->height;
@@ -1428,6 +1708,8 @@ static int ensureOutputs(KfrtContext* ctx, uint32_t nCams, uint32_t w, uint32_t 
 static SceneDev sceneDev(KfrtContext* ctx) {
   SceneDev sc{};
   sc.tlasNodes = ctx->nTlasNodes ? ctx->tlasNodes.p : nullptr;
+  sc.wsiNodes = ctx->wsiValid ? ctx->wsiNodes.p : nullptr;
+  sc.wsiTris = ctx->wsiValid ? ctx->wsiTris.p : nullptr;
   sc.inst = ctx->instRec.p;
   sc.instSsbo = ctx->instDev.p;
   sc.geoms = ctx->geomTable.p;
@@ -1461,6 +1743,10 @@ int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, u
   }
   int rc = ensureOutputs(ctx, nCameras, width, height);
   if (rc) return rc;
+  if (ctx->wsiDirty) {
+    rc = buildWsi(ctx);
+    if (rc) return rc;
+  }
   KF_CUDA(ctx, cudaMemcpyAsync(ctx->cams.p, cameras, sizeof(KfrtCamera) * nCameras, cudaMemcpyHostToDevice, ctx->stream));
   KF_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * 16, ctx->stream));
   RenderArgs a;
@@ -1481,6 +1767,11 @@ int kfrtRender(KfrtContext* ctx, const KfrtCamera* cameras, uint32_t nCameras, u
   a.depth = ctx->depth.p;
   a.counters = ctx->counters.p;
   ctx->stageUsed = 0;
+  if (ctx->wsiMode == 1 && ctx->wsiValid && ctx->wsiChoice == 0 && sampleEnd > sampleBegin) {
+    rc = probeStructures(ctx, a);
+    if (rc) return rc;
+    a.sc = sceneDev(ctx);
+  }
   rc = renderWavefront(ctx, a);
   if (rc) return rc;
   ctx->lastPc = *pc;

@@ -39,6 +39,7 @@ def load():
         "kfrtSetEnvironmentCube": [vp, C.POINTER(vp), u32], "kfrtClearEnvironment": [vp],
         "kfrtSetLights": [vp, vp, vp, vp], "kfrtBuildBlas": [vp], "kfrtSetInstances": [vp, vp, u32],
         "kfrtBuildTlas": [vp], "kfrtRefitTlas": [vp, vp, u32], "kfrtGetBvhStats": [vp, vp],
+        "kfrtSetInstanceSubtrees": [vp, i32, C.c_uint64],
         "kfrtRender": [vp, vp, u32, u32, u32, vp, u32, u32, u32], "kfrtResolve": [vp],
         "kfrtReduceNccl": [vp, vp, i32], "kfrtDownloadBGRA8": [vp, u32, vp, sz],
         "kfrtMapBGRA8": [vp, u32, C.POINTER(vp), C.POINTER(sz)],
@@ -170,6 +171,10 @@ class Context:
     def refit_tlas(self, transforms):
         t = _arr(transforms, "<f4").reshape(-1, 16)
         self._ck(self.lib.kfrtRefitTlas(self.h, _ptr(t), t.shape[0]))
+
+    def set_instance_subtrees(self, mode, max_triangles=0):
+        """0: two-level structure only; 1: world-space instance subtrees when the scene fits the budget (default)."""
+        self._ck(self.lib.kfrtSetInstanceSubtrees(self.h, int(mode), int(max_triangles)))
 
     def bvh_stats(self):
         s = np.zeros((), wire.BVH_STATS)

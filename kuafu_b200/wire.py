@@ -31,12 +31,14 @@ COUNTERS = np.dtype([("paths", "<u8"), ("extensionRays", "<u8"), ("shadowRays", 
 BVH_STATS = np.dtype([("blasCount", "<u4"), ("instanceCount", "<u4"), ("triangleCount", "<u8"),
                       ("instancedTriangles", "<u8"), ("blasNodeCount", "<u8"),
                       ("tlasNodeCount", "<u8"), ("nodeBytes", "<u4"), ("triangleBytes", "<u4"),
-                      ("instanceBytes", "<u4"), ("tlasRebuilds", "<u4")])
+                      ("instanceBytes", "<u4"), ("tlasRebuilds", "<u4"),
+                      ("subtreeNodeCount", "<u8"), ("subtreeTriangles", "<u8"), ("subtreeDepth", "<u4"),
+                      ("subtreeBuilds", "<u4")])
 
 assert VERTEX.itemsize == 48 and MATERIAL.itemsize == 80 and INSTANCE.itemsize == 80
 assert CAMERA.itemsize == 320 and DIRECTIONAL_LIGHT.itemsize == 32
 assert POINT_LIGHTS.itemsize == 1024 and ACTIVE_LIGHTS.itemsize == 1536
-assert PUSH_CONSTANTS.itemsize == 48 and COUNTERS.itemsize == 128 and BVH_STATS.itemsize == 56
+assert PUSH_CONSTANTS.itemsize == 48 and COUNTERS.itemsize == 128 and BVH_STATS.itemsize == 80
 
 AUX_RGBA32F, AUX_ALBEDO32F, AUX_NORMAL32F, AUX_HIT_IDS, AUX_HIT_T = 0, 1, 2, 3, 4
 AUX_DEPTH, AUX_SEGMENTATION, AUX_SUM32F, AUX_BGRA8 = 5, 6, 7, 8

@@ -155,6 +155,7 @@ def test_device_top_level_build_quality(mods, name, w, h, limit):
     r = host.Renderer(device=0, accumulate=False)
     r.load_scene(name, w, h, 2)
     ctx = rt.Context(handle=r.device_context())
+    ctx.set_instance_subtrees(0)  # the two-level walk counts its top-level node steps separately
     r.run()
     ctx.set_detail_counters(True)
     r.run()

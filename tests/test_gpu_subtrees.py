@@ -1,0 +1,103 @@
+"""World-space instance subtrees (kf_wsi.cuh, kfrtSetInstanceSubtrees) against the two-level structure and the
+oracle: the two structures must give the SAME buffers bit for bit -- hit ids, t, depth, and the radiance sums
+too, because every path takes the same decisions on the same hits."""
+import numpy as np
+import pytest
+
+import parity
+import pyscene
+from kuafu_b200 import wire
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    from kuafu_b200 import rt as _rt
+    return _rt
+
+
+@pytest.fixture(scope="module")
+def orc_mod():
+    from oracle import oracle
+    return oracle
+
+
+def _buffers(ctx, sc, clock_base=3):
+    ctx.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, None, clock_base)
+    n = len(sc.cams)
+    out = {k: np.stack([ctx.download_aux(a, c) for c in range(n)])
+           for k, a in (("sum", wire.AUX_SUM32F), ("hit_ids", wire.AUX_HIT_IDS), ("hit_t", wire.AUX_HIT_T),
+                        ("depth", wire.AUX_DEPTH), ("albedo", wire.AUX_ALBEDO32F), ("normal", wire.AUX_NORMAL32F))}
+    cnt = ctx.counters()
+    out["counters"] = {k: int(cnt[k]) for k in ("paths", "extensionRays", "shadowRays", "extensionHits")}
+    return out
+
+
+def _same(a, b):
+    for k in ("hit_ids", "hit_t", "depth", "sum", "albedo", "normal"):
+        assert np.array_equal(a[k].view(np.uint32) if a[k].dtype == np.float32 else a[k],
+                              b[k].view(np.uint32) if b[k].dtype == np.float32 else b[k]), k
+    assert a["counters"] == b["counters"]
+
+
+@pytest.mark.parametrize("lights,textures", [("dir", True), ("dir point active", True), ("point", False)])
+def test_subtrees_equal_two_level_and_oracle(rt, orc_mod, lights, textures):
+    sc = pyscene.small_scene(seed=5, w=160, h=120, spp=3, depth=6, lights=lights, textures=textures)
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    ctx.set_instance_subtrees(0)
+    two = _buffers(ctx, sc)
+    assert int(ctx.bvh_stats()["subtreeNodeCount"]) == 0
+    ctx.set_instance_subtrees(2)
+    sub = _buffers(ctx, sc)
+    st = ctx.bvh_stats()
+    assert int(st["subtreeNodeCount"]) > 0 and int(st["subtreeTriangles"]) == int(st["instancedTriangles"])
+    _same(two, sub)
+    orc = orc_mod.Oracle()
+    sc.upload(orc)
+    ref = orc.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, None, 3)
+    parity.assert_hits_bit_exact(sub, ref)
+    ctx.close()
+
+
+def test_subtrees_follow_refit_and_probe_picks_one(rt):
+    """Mode 2 rebuilds the subtrees after kfrtRefitTlas; mode 1 (the default) probes a freshly built scene
+    once, keeps one structure, and leaves a scene that is being refitted on the two-level walk."""
+    sc = pyscene.small_scene(seed=7, w=128, h=96, spp=2, depth=5, lights="dir", textures=True)
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    insts = np.array(sc.insts, wire.INSTANCE)
+    moved = np.array(insts["transform"], "<f4").reshape(-1, 16).copy()
+    moved[1:, 12:15] += np.float32(0.125)
+    ctx.set_instance_subtrees(2)
+    ctx.refit_tlas(moved)
+    sub = _buffers(ctx, sc)
+    builds = int(ctx.bvh_stats()["subtreeBuilds"])
+    assert builds >= 1 and int(ctx.bvh_stats()["subtreeNodeCount"]) > 0
+    ctx.set_instance_subtrees(0)
+    two = _buffers(ctx, sc)
+    _same(two, sub)
+    # default mode: a moving scene is not probed
+    ctx.set_instance_subtrees(1)
+    ctx.refit_tlas(moved)
+    auto = _buffers(ctx, sc)
+    assert int(ctx.bvh_stats()["subtreeNodeCount"]) == 0
+    _same(two, auto)
+    # after a full build the probe runs once and the frame it precedes is unchanged
+    ctx.set_instances(insts)
+    ctx.build_tlas()
+    first = _buffers(ctx, sc)
+    again = _buffers(ctx, sc)
+    _same(first, again)
+    ctx.close()
+
+
+def test_budget_keeps_large_scenes_two_level(rt):
+    sc = pyscene.small_scene(seed=3, w=64, h=48, spp=1, depth=3, lights="dir", textures=False)
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    ctx.set_instance_subtrees(2, max_triangles=8)  # far below the scene's triangle count
+    _buffers(ctx, sc)
+    assert int(ctx.bvh_stats()["subtreeNodeCount"]) == 0
+    ctx.close()
