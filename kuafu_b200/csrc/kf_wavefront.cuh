@@ -82,11 +82,6 @@ KF_D void slotToPixel(const WfArgs& a, uint32_t pixelSlot, uint32_t& cam, uint32
   y = ty * 4 + (lane >> 3);
 }
 
-KF_D void countAdd(unsigned long long* c, bool pred) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-  if ((threadIdx.x & 31) == 0 && mask) atomicAdd(c, (unsigned long long)__popc(mask));
-}
-
 // ---------------------------------------------------------------------------------------------
 // One thread per pixel slot, looping over the samples of the batch: the pixel's seed hash (shared by all
 // samples, rgen:23) is made once and its jitter stream advanced two draws per sample instead of being
@@ -94,38 +89,54 @@ KF_D void countAdd(unsigned long long* c, bool pred) {
 // consecutive pixels of one sample followed by the same pixels of the next sample -- rays that walk the
 // same part of the hierarchy sit next to each other in the first traversal stage.
 __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
-  const uint32_t stride = gridDim.x * blockDim.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.b.counts[1] = 0;
     a.b.counts[2] = 0;
     a.b.counts[3] = 0;
   }
-  for (uint32_t base = blockIdx.x * blockDim.x; base < a.slotsPerSample; base += stride) {
-    const uint32_t pixelSlot = base + threadIdx.x;
-    bool valid = pixelSlot < a.slotsPerSample;
-    uint32_t cam = 0, x = 0, y = 0;
-    if (valid) {
-      slotToPixel(a, pixelSlot, cam, x, y);
-      valid = x < a.w && y < a.h;
-    }
-    const uint32_t mapping = y * a.w + x;
-    // the pixel-jitter stream is shared by all samples of the pixel (rgen:30-37): skip the two draws of
-    // each sample before this batch once, then two draws per sample
-    uint32_t seed = valid ? lcgSkip(tea(mapping, a.clockBase), 2u * a.batchBegin) : 0u;
-    for (uint32_t s = 0; s < a.batchCount; s++) {
-      const uint32_t slot = s * a.slotsPerSample + pixelSlot;
-      if (valid) {
-        const uint32_t i = a.batchBegin + s;  // global sample index
-        uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
-        V3 o, d;
-        cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);  // draws the sample's two jitter numbers from seed
-        a.b.rayO[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-        a.b.rayD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-        a.b.stateW[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(raySeed));
-        a.b.stateC[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      }
-      queueAppend(a.b.queue[0], a.b.counts + 0, valid, slot);
-    }
+  const uint32_t pixelSlot = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = pixelSlot < a.slotsPerSample;
+  uint32_t cam = 0, x = 0, y = 0;
+  if (valid) {
+    slotToPixel(a, pixelSlot, cam, x, y);
+    valid = x < a.w && y < a.h;
+  }
+  // Queue positions: the block reserves room for all its pixels x all samples of the batch with ONE atomic
+  // (a warp-aggregated append per sample was a million atomics on one address per launch) and lays its
+  // entries out sample by sample -- runs of up to 256 consecutive pixels of one sample followed by the same
+  // pixels of the next one, the order the first traversal and shade stages like.
+  __shared__ uint32_t sWarpValid[8];
+  __shared__ uint32_t sBase;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) sWarpValid[warp] = __popc(validMask);
+  __syncthreads();
+  uint32_t before = 0, blockValid = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < 8; w++) {
+    const uint32_t v = sWarpValid[w];
+    if (w < warp) before += v;
+    blockValid += v;
+  }
+  if (threadIdx.x == 0) sBase = atomicAdd(a.b.counts + 0, blockValid * a.batchCount);
+  __syncthreads();
+  if (!valid) return;
+  const uint32_t rank = before + __popc(validMask & ((1u << lane) - 1u));
+  const uint32_t mapping = y * a.w + x;
+  // the pixel-jitter stream is shared by all samples of the pixel (rgen:30-37): skip the two draws of
+  // each sample before this batch once, then two draws per sample
+  uint32_t seed = lcgSkip(tea(mapping, a.clockBase), 2u * a.batchBegin);
+  for (uint32_t s = 0; s < a.batchCount; s++) {
+    const uint32_t slot = s * a.slotsPerSample + pixelSlot;
+    const uint32_t i = a.batchBegin + s;  // global sample index
+    uint32_t raySeed = tea(mapping, a.clockBase + 1u + i);
+    V3 o, d;
+    cameraRay(a.cams + cam, x, y, a.w, a.h, seed, raySeed, o, d);  // draws the sample's two jitter numbers from seed
+    a.b.rayO[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+    a.b.rayD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    a.b.stateW[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(raySeed));
+    a.b.stateC[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    a.b.queue[0][sBase + s * blockValid + rank] = slot;
   }
 }
 
@@ -158,6 +169,7 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
   const uint32_t* __restrict__ queue = a.b.queue[q];
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
+  uint32_t hitTotal = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.b.counts[4] = 0;  // fetch cursors of the next closest-hit / occlusion stages
     a.b.counts[5] = 0;
@@ -338,8 +350,11 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
     }
     queueAppend(a.b.queue[q ^ 1], a.b.counts + (q ^ 1), toNext, slot);
     queueAppend(a.b.shadowQueue[0], a.b.counts + 2, toShadow, slot);
-    countAdd(a.counters + 3, isHit);
+    hitTotal += isHit ? 1u : 0u;
   }
+  // (one atomic per warp for the whole launch: per round it was one more serialised same-address atomic)
+  hitTotal = __reduce_add_sync(0xffffffffu, hitTotal);
+  if ((threadIdx.x & 31u) == 0u && hitTotal) atomicAdd(a.counters + 3, (unsigned long long)hitTotal);
   if (DETAIL) atomicAdd(a.counters + 7, texTotal);
 }
 
