@@ -233,7 +233,7 @@ struct KfrtContext {
   uint64_t launches = 0;
   // wavefront scheduler state
   int numSMs = 148;
-  size_t batchSlotTarget = size_t(64) << 20;  // measured on config 3: 32 Mi -> 64 Mi slots +0.8 %, 128 Mi no further gain
+  size_t batchSlotTarget = size_t(64) << 20;  // path slots per batch (144 B each).  Measured on config 3 at the end of round 2 (ms per 64-spp frame): 16 Mi 213.1, 32 Mi 208.1, 64 Mi 205.7, 128 Mi 204.5 -- for 10 GB more path state and 0.45 s more in the first frame (its allocation)
   bool traceLog = false;  // KFRT_TRACE_LOG=1: per-launch ray count and time of every traversal stage on stderr
   size_t wfSlots = 0;
   bool wfMulti = false;
@@ -1452,20 +1452,9 @@ static void launchTrace(KfrtContext* ctx, const TraceArgs& te, bool any, bool de
   }
 }
 
-static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
-  const uint32_t tilesX = (ra.w + 7) / 8, tilesY = (ra.h + 3) / 4;
-  const size_t slotsPerSample = size_t(ra.nCams) * tilesX * tilesY * 32;
-  const uint32_t nSamples = ra.s1 - ra.s0;
-  ctx->launches = 0;
-  if (nSamples == 0) {
-    KF_CUDA(ctx, cudaMemsetAsync(ra.sum, 0, sizeof(float4) * size_t(ra.nCams) * ra.w * ra.h, ctx->stream));
-    return KFRT_OK;
-  }
-  uint32_t batch = uint32_t(std::max<size_t>(1, ctx->batchSlotTarget / slotsPerSample));
-  batch = std::min(batch, nSamples);
-  const size_t slots = slotsPerSample * batch;
+// Path-state buffers of the wavefront scheduler for `slots` path slots (they only ever grow).
+static int ensurePathState(KfrtContext* ctx, size_t slots, bool multi) {
   if (slots >= (size_t(1) << 31)) KF_FAIL(ctx, KFRT_ERR_INVALID, "too many pixels for one batch");
-  const bool multi = ctx->nLightSlots > 1;
   KF_CUDA(ctx, ctx->wfRayO.ensure(slots));
   KF_CUDA(ctx, ctx->wfRayD.ensure(slots));
   KF_CUDA(ctx, ctx->wfHitA.ensure(slots));
@@ -1480,6 +1469,25 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   KF_CUDA(ctx, ctx->wfShadowQ0.ensure(slots));
   if (multi) KF_CUDA(ctx, ctx->wfShadowQ1.ensure(slots));
   KF_CUDA(ctx, ctx->wfCounts.ensure(8));
+  return KFRT_OK;
+}
+
+static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
+  const uint32_t tilesX = (ra.w + 7) / 8, tilesY = (ra.h + 3) / 4;
+  const size_t slotsPerSample = size_t(ra.nCams) * tilesX * tilesY * 32;
+  const uint32_t nSamples = ra.s1 - ra.s0;
+  ctx->launches = 0;
+  if (nSamples == 0) {
+    KF_CUDA(ctx, cudaMemsetAsync(ra.sum, 0, sizeof(float4) * size_t(ra.nCams) * ra.w * ra.h, ctx->stream));
+    return KFRT_OK;
+  }
+  uint32_t batch = uint32_t(std::max<size_t>(1, ctx->batchSlotTarget / slotsPerSample));
+  batch = std::min(batch, nSamples);
+  const bool multi = ctx->nLightSlots > 1;
+  {
+    int rc = ensurePathState(ctx, slotsPerSample * batch, multi);
+    if (rc) return rc;
+  }
   if (!ctx->gridTrace[0]) {
     ctx->gridTrace[0] = persistentGrid(ctx, k_wf_trace<false, false>, 128);
     ctx->gridTrace[1] = persistentGrid(ctx, k_wf_trace<false, true>, 128);
@@ -1653,15 +1661,24 @@ static int probeStructures(KfrtContext* ctx, const RenderArgs& full) {
   KF_CUDA(ctx, cudaEventCreate(&ev[0]));
   KF_CUDA(ctx, cudaEventCreate(&ev[1]));
   float ms[2] = {3.0e38f, 3.0e38f};
+  // the path state of the frame proper is sized first (so that no allocation falls into a timed pass), and a
+  // one-sample pass with each structure has loaded its kernels
   int rc = KFRT_OK;
-  for (int which = 1; which >= 0 && rc == KFRT_OK; which--) {  // (the first one also pays the path-state allocation)
-    for (int pass = 0; pass < (which == 1 ? 2 : 1) && rc == KFRT_OK; pass++) {
-      p.sc.wsiNodes = which ? ctx->wsiNodes.p : nullptr;
-      p.sc.wsiTris = which ? ctx->wsiTris.p : nullptr;
+  {
+    const uint32_t nSamples = full.s1 - full.s0;
+    const uint32_t batch = std::min(uint32_t(std::max<size_t>(1, ctx->batchSlotTarget / slotsPerSample)), nSamples);
+    rc = ensurePathState(ctx, slotsPerSample * batch, ctx->nLightSlots > 1);
+  }
+  for (int pass = 0; pass < 2 && rc == KFRT_OK; pass++) {
+    RenderArgs q = p;
+    if (pass == 0) q.s1 = q.s0 + 1;
+    for (int which = 0; which < 2 && rc == KFRT_OK; which++) {
+      q.sc.wsiNodes = which ? ctx->wsiNodes.p : nullptr;
+      q.sc.wsiTris = which ? ctx->wsiTris.p : nullptr;
       cudaEventRecord(ev[0], ctx->stream);
-      rc = renderWavefront(ctx, p);
+      rc = renderWavefront(ctx, q);
       cudaEventRecord(ev[1], ctx->stream);
-      if (rc == KFRT_OK && cudaEventSynchronize(ev[1]) == cudaSuccess) cudaEventElapsedTime(&ms[which], ev[0], ev[1]);
+      if (rc == KFRT_OK && pass == 1 && cudaEventSynchronize(ev[1]) == cudaSuccess) cudaEventElapsedTime(&ms[which], ev[0], ev[1]);
     }
   }
   cudaEventDestroy(ev[0]);

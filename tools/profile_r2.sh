@@ -6,6 +6,9 @@
 #   r2_shade.ncu-rep       --set full of k_wf_shade (depth 1) and k_wf_shadow_resolve
 #   r2_unique_traffic.csv / r2_unique10m_traffic.csv   dram bytes of the traversal launches on the un-instanced stress scenes
 set -x
+# the structure probe (kfrtSetInstanceSubtrees mode 1) picks the two-level structure for config 3; it is switched
+# off here so that the captures below see the kernels of the frame, not those of the probe
+export KFRT_INSTANCE_SUBTREES=0
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --spp 32 --no-cpu-baseline"
 CMD8="python bench.py --steps 1 --warmup 1 --spp 8 --no-cpu-baseline"
