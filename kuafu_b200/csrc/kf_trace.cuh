@@ -35,7 +35,9 @@ namespace kf {
 // iteration: 0.4 % of the stage); re-measured in round 2 after the node test got cheaper: 6 / 10 / 12 idle
 // lanes and periods 1 / 3 all lose 0.2 - 3 %.
 #define KF_INST_PERIOD 2  // measured on config 3: 1 -> 2 takes 2.8 % off the closest-hit stage, 4 loses it again
+#ifndef KF_REFILL_IDLE
 #define KF_REFILL_IDLE 8  // refill the warp once this many lanes are without a ray
+#endif
 
 struct TraceArgs {
   SceneDev sc;

@@ -18,7 +18,7 @@
 // structure holds); every node of a subtree carries its instance index, and the lane keeps the
 // object-space ray of the instance it tested last (world -> object with the oracle's fused expressions,
 // traceInstance()), re-deriving it when a triangle of another instance comes up.  World boxes are padded
-// by 2^-15 of the largest coordinate -- some 40x the worst disagreement between the world-space ray and the
+// by 2^-14 of the largest coordinate (boxPad) -- some 80x the worst disagreement between the world-space ray and the
 // object-space one -- so that no triangle the object-space test accepts is culled by a world-space box.
 //
 // Scenes over the budget (config 5: 10 M instanced triangles) and scenes with more than 1 024 visible
