@@ -680,6 +680,10 @@ def main():
                        "instances": int(stats["instanceCount"])},
             "per_gpu_mrays": value / world,
             "rays_per_step": rays_total / args.steps,
+            # light samples whose occlusion ray cannot change colour or RNG state (a transmissive surface seen from
+            # inside) are answered in the shade stage; the reference traces them.  They are NOT in rays_per_step or
+            # in `value`: only rays that were traversed count (rank 0's share shown)
+            "light_samples_not_traced_per_step_rank0": sum(int(c["shadowRaysSkipped"]) for c in counters) / args.steps,
             "first_frame_ms": first_frame_ms, "frame_check": frame_check,
             "traversal_structure": "instance subtrees" if int(stats["subtreeNodeCount"]) else "two-level",
             "roofline": roof, "cpu_baseline": cpu,

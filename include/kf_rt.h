@@ -142,7 +142,8 @@ typedef struct KfrtCounters {
   uint64_t shadowInstanceVisits; /* the occlusion-ray share of instanceVisits (detail) */
   uint64_t tlasNodeVisits;       /* the top-level share of nodeVisits, both ray kinds (detail) */
   uint64_t instanceEntries;      /* instanceVisits whose world-box re-test passed: BLAS traversals (detail) */
-  uint64_t reserved[2];
+  uint64_t shadowRaysSkipped;    /* light samples whose occlusion ray could not change colour or RNG state and was not traced (not in shadowRays) */
+  uint64_t reserved[1];
 } KfrtCounters;
 
 /* BVH statistics for the roofline accounting in DESIGN.md. */

@@ -1988,6 +1988,7 @@ int kfrtGetCounters(KfrtContext* ctx, KfrtCounters* out) {
   out->textureFetches = h[7];
   out->tlasNodeVisits = h[12];
   out->instanceEntries = h[13];
+  out->shadowRaysSkipped = h[11];
   out->kernelLaunches = ctx->launches;
   return KFRT_OK;
 }

@@ -140,6 +140,24 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
   }
 }
 
+// The next light whose occlusion ray can matter, with its speculative contribution.  A light that would
+// contribute exactly nothing AND draws no random number in calcDirect (a surface of a transmissive material
+// seen from inside: PathTrace.rchit:103-171 returns zero before its first draw) leaves colour and seed the
+// same whether its ray is occluded or not, so the ray is not traced: 21 % of the occlusion rays of config 3,
+// whose glass spheres are lit from inside by every path that crosses them.  Such rays are counted in
+// counters[11] (KfrtCounters.shadowRaysSkipped), not in shadowRays.
+KF_D bool nextRelevantLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& k, V3& L, float& maxDist,
+                            V3& lightEmission, uint32_t& texFetches, V3& contrib, uint32_t& specSeed, uint32_t& skipped) {
+  while (nextLight(sc, sf, seed, k, L, maxDist, lightEmission, texFetches)) {
+    specSeed = seed;
+    contrib = calcDirect(sf, L, lightEmission, specSeed);
+    if (anyNe(contrib, mk3(0.0f)) || specSeed != seed) return true;
+    skipped++;
+    k++;
+  }
+  return false;
+}
+
 KF_D void storeCtx(float4* __restrict__ c, const Surface& sf, int k, V3 acc) {
   c[0] = make_float4(sf.N.x, sf.N.y, sf.N.z, sf.f);
   c[1] = make_float4(sf.V.x, sf.V.y, sf.V.z, sf.a2);
@@ -169,7 +187,7 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
   const uint32_t* __restrict__ queue = a.b.queue[q];
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
-  uint32_t hitTotal = 0;
+  uint32_t hitTotal = 0, skipTotal = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.b.counts[4] = 0;  // fetch cursors of the next closest-hit / occlusion stages
     a.b.counts[5] = 0;
@@ -328,11 +346,11 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           a.b.rayO[slot] = make_float4(sf.worldPos.x, sf.worldPos.y, sf.worldPos.z, 0.0f);
           a.b.rayD[slot] = make_float4(L.x, L.y, L.z, 0.0f);
           int k = 0;
-          V3 Ls, le;
+          V3 Ls, le, contrib = mk3(0.0f);
           float maxDist;
-          if (nextLight(a.sc, sf, seed, k, Ls, maxDist, le, tex)) {
-            uint32_t specSeed = seed;
-            const V3 contrib = calcDirect(sf, Ls, le, specSeed);
+          uint32_t specSeed = seed;
+          const bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal);
+          if (need) {
             a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
             a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
             if (MULTI) storeCtx(a.b.ctx + size_t(6) * slot, sf, k, mk3(0.0f));
@@ -354,7 +372,9 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
   }
   // (one atomic per warp for the whole launch: per round it was one more serialised same-address atomic)
   hitTotal = __reduce_add_sync(0xffffffffu, hitTotal);
+  skipTotal = __reduce_add_sync(0xffffffffu, skipTotal);
   if ((threadIdx.x & 31u) == 0u && hitTotal) atomicAdd(a.counters + 3, (unsigned long long)hitTotal);
+  if ((threadIdx.x & 31u) == 0u && skipTotal) atomicAdd(a.counters + 11, (unsigned long long)skipTotal);
   if (DETAIL) atomicAdd(a.counters + 7, texTotal);
 }
 
@@ -367,6 +387,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
   if (blockIdx.x == 0 && threadIdx.x == 0) a.b.counts[5] = 0;  // occlusion fetch cursor of the next round
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long texTotal = 0;
+  uint32_t skipTotal = 0;
   __shared__ uint32_t sCnt[2][8];
   __shared__ uint32_t sBase[2];
   uint32_t appendRound = 0;
@@ -414,9 +435,9 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
         V3 Ls, le;
         float maxDist;
         uint32_t tex = 0;
-        if (nextLight(a.sc, sf, seed, k, Ls, maxDist, le, tex)) {
-          uint32_t specSeed = seed;
-          const V3 contrib = calcDirect(sf, Ls, le, specSeed);
+        V3 contrib = mk3(0.0f);
+        uint32_t specSeed = seed;
+        if (nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal)) {
           a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
           a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
           storeCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);
@@ -445,6 +466,10 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
     queueAppendBlock(a.b.queue[qNext], a.b.counts + qNext, toNext, slot, sCnt, sBase, appendRound);
     appendRound ^= 1u;
     if (MULTI) queueAppend(a.b.shadowQueue[sq ^ 1], a.b.counts + 2 + (sq ^ 1), toShadow, slot);
+  }
+  if (MULTI) {
+    skipTotal = __reduce_add_sync(0xffffffffu, skipTotal);
+    if ((threadIdx.x & 31u) == 0u && skipTotal) atomicAdd(a.counters + 11, (unsigned long long)skipTotal);
   }
   if (DETAIL && MULTI) atomicAdd(a.counters + 7, texTotal);
 }

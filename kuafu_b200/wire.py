@@ -27,7 +27,7 @@ COUNTERS = np.dtype([("paths", "<u8"), ("extensionRays", "<u8"), ("shadowRays", 
                      ("extensionHits", "<u8"), ("nodeVisits", "<u8"), ("triangleTests", "<u8"),
                      ("instanceVisits", "<u8"), ("textureFetches", "<u8"), ("kernelLaunches", "<u8"),
                      ("shadowNodeVisits", "<u8"), ("shadowTriangleTests", "<u8"), ("shadowInstanceVisits", "<u8"),
-                     ("tlasNodeVisits", "<u8"), ("instanceEntries", "<u8"), ("reserved", "<u8", 2)])
+                     ("tlasNodeVisits", "<u8"), ("instanceEntries", "<u8"), ("shadowRaysSkipped", "<u8"), ("reserved", "<u8", 1)])
 BVH_STATS = np.dtype([("blasCount", "<u4"), ("instanceCount", "<u4"), ("triangleCount", "<u8"),
                       ("instancedTriangles", "<u8"), ("blasNodeCount", "<u8"),
                       ("tlasNodeCount", "<u8"), ("nodeBytes", "<u4"), ("triangleBytes", "<u4"),

@@ -19,6 +19,10 @@ def render_both(sc, ctx, orc, clock_base=3, sample_begin=0, sample_end=None, bru
     }
     cnt = ctx.counters()
     got["counters"] = {k: int(cnt[k]) for k in ("paths", "extensionRays", "shadowRays", "extensionHits")}
+    # light samples whose occlusion ray cannot change the image are not traced by the CUDA path (kf_wavefront.cuh,
+    # nextRelevantLight); the oracle, like the reference, traces them: they count as shadow rays in comparisons
+    got["counters"]["shadowRaysTraced"] = got["counters"]["shadowRays"]
+    got["counters"]["shadowRays"] += int(cnt["shadowRaysSkipped"])
     return got, ref
 
 

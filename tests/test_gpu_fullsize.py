@@ -49,8 +49,11 @@ def test_config3_full_frame_hit_buffers(mods):
     st = parity.radiance_stats(got["sum"], ref["sum"], 1)
     assert st["frac_gt_1e-3"] < 0.02 and st["mean_rel_diff"] < 2e-3, st
     assert int(cnt["paths"]) == ref["counters"]["paths"] == w * h
-    for k in ("extensionRays", "shadowRays", "extensionHits"):
-        assert abs(int(cnt[k]) - ref["counters"][k]) <= 0.02 * ref["counters"][k], (k, int(cnt[k]), ref["counters"][k])
+    mine = {k: int(cnt[k]) for k in ("extensionRays", "shadowRays", "extensionHits")}
+    mine["shadowRays"] += int(cnt["shadowRaysSkipped"])  # (light samples whose ray cannot matter are not traced here)
+    assert int(cnt["shadowRaysSkipped"]) > 0.1 * mine["shadowRays"], "config 3's glass spheres: a fifth of the light samples"
+    for k in mine:
+        assert abs(mine[k] - ref["counters"][k]) <= 0.02 * ref["counters"][k], (k, mine[k], ref["counters"][k])
     r.close()
 
 
