@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           float maxDist;
           uint32_t specSeed = seed;
           bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal);
-#ifndef KF_NO_DEAD_PATH_SKIP
           // A path whose weight the BSDF sample has just taken to exactly zero (a GGX direction below the
           // horizon, rchit:420-428) adds `shadow_color * 0` and then ends before its next random draw
           // (rgen:119): its light sample cannot matter either, unless the contribution is not finite.
@@ -358,7 +357,6 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
             need = false;
             skipTotal++;
           }
-#endif
           if (need) {
             a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
             a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
