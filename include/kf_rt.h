@@ -256,6 +256,12 @@ KFRT_API int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n
  * current budget (default 4 Mi).  Environment overrides at kfrtCreate: KFRT_INSTANCE_SUBTREES,
  * KFRT_INSTANCE_SUBTREES_MAX_TRIS. */
 KFRT_API int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTriangles);
+/* Light samples whose occlusion ray cannot change the image -- a contribution of exactly zero that draws no
+ * random number (PathTrace.rchit:107-108: a transmissive surface seen from inside), or any sample of a path
+ * whose weight the BSDF has just taken to zero (rgen:119 ends it before its next draw) -- are answered without
+ * a ray and counted in KfrtCounters.shadowRaysSkipped (on: 1, the default).  0 traces every light sample the
+ * reference traces: same buffers bit for bit, shadowRays larger by exactly shadowRaysSkipped. */
+KFRT_API int kfrtSetLightSampleCulling(KfrtContext* ctx, int on);
 KFRT_API int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out);
 
 /* ------------------------------------------------------------------------------------------------

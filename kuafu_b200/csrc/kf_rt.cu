@@ -195,6 +195,7 @@ struct KfrtContext {
 
   // world-space instance subtrees (kf_wsi.cuh): built lazily by the first kfrtRender after the instance
   // set or a transform has changed, when the instanced triangles fit the budget
+  bool cullLightSamples = true;  // kfrtSetLightSampleCulling
   int wsiMode = 1;  // 0 never; 1 static scenes within the budget, if a timed probe says they are faster; 2 whenever they fit
   uint64_t wsiMaxTris = uint64_t(4) << 20;
   bool wsiValid = false, wsiDirty = true;
@@ -1376,6 +1377,12 @@ int kfrtRefitTlas(KfrtContext* ctx, const float* transforms, uint32_t n) {
   return KFRT_OK;
 }
 
+int kfrtSetLightSampleCulling(KfrtContext* ctx, int on) {
+  KF_CHECK_CTX(ctx);
+  ctx->cullLightSamples = on != 0;
+  return KFRT_OK;
+}
+
 int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTriangles) {
   KF_CHECK_CTX(ctx);
   if (mode < 0 || mode > 2) KF_FAIL(ctx, KFRT_ERR_INVALID, "instance-subtree mode must be 0, 1 or 2");
@@ -1531,6 +1538,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   a.tilesY = tilesY;
   a.slotsPerSample = uint32_t(slotsPerSample);
   a.firstSample = ra.s0;
+  a.cullLightSamples = ctx->cullLightSamples ? 1u : 0u;
   a.pc = ra.pc;
   a.clockBase = ra.clockBase;
   a.sum = ra.sum;

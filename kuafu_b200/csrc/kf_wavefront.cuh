@@ -60,6 +60,7 @@ struct WfArgs {
   uint32_t slotsPerSample;               // nCams * tilesX * tilesY * 32
   uint32_t batchBegin, batchCount;       // global sample index of the first sample, samples in batch
   uint32_t firstSample;                  // sampleBegin of the kfrtRender call
+  uint32_t cullLightSamples;             // 1: light samples whose occlusion ray cannot matter are not traced (nextRelevantLight)
   KfrtPushConstants pc;
   uint32_t clockBase;
   float4* sum;
@@ -147,11 +148,12 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
 // whose glass spheres are lit from inside by every path that crosses them.  Such rays are counted in
 // counters[11] (KfrtCounters.shadowRaysSkipped), not in shadowRays.
 KF_D bool nextRelevantLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& k, V3& L, float& maxDist,
-                            V3& lightEmission, uint32_t& texFetches, V3& contrib, uint32_t& specSeed, uint32_t& skipped) {
+                            V3& lightEmission, uint32_t& texFetches, V3& contrib, uint32_t& specSeed, uint32_t& skipped,
+                            bool cull) {
   while (nextLight(sc, sf, seed, k, L, maxDist, lightEmission, texFetches)) {
     specSeed = seed;
     contrib = calcDirect(sf, L, lightEmission, specSeed);
-    if (anyNe(contrib, mk3(0.0f)) || specSeed != seed) return true;
+    if (!cull || anyNe(contrib, mk3(0.0f)) || specSeed != seed) return true;
     skipped++;
     k++;
   }
@@ -349,11 +351,11 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           V3 Ls, le, contrib = mk3(0.0f);
           float maxDist;
           uint32_t specSeed = seed;
-          bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal);
+          bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, a.cullLightSamples != 0u);
           // A path whose weight the BSDF sample has just taken to exactly zero (a GGX direction below the
           // horizon, rchit:420-428) adds `shadow_color * 0` and then ends before its next random draw
           // (rgen:119): its light sample cannot matter either, unless the contribution is not finite.
-          if (!MULTI && need && allEq(weight, mk3(0.0f)) && finite3(contrib)) {
+          if (!MULTI && need && a.cullLightSamples && allEq(weight, mk3(0.0f)) && finite3(contrib)) {
             need = false;
             skipTotal++;
           }
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
         uint32_t tex = 0;
         V3 contrib = mk3(0.0f);
         uint32_t specSeed = seed;
-        if (nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal)) {
+        if (nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, a.cullLightSamples != 0u)) {
           a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
           a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
           storeCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);

@@ -101,3 +101,29 @@ def test_budget_keeps_large_scenes_two_level(rt):
     _buffers(ctx, sc)
     assert int(ctx.bvh_stats()["subtreeNodeCount"]) == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("lights", ["dir", "dir point active"])
+def test_culled_light_samples_change_nothing(rt, lights):
+    """kfrtSetLightSampleCulling: with the culling off every light sample the reference traces is traced; with
+    it on (the default) the same buffers come out bit for bit, and the traced + skipped light samples add up
+    to exactly the number traced without it.  The scene has a glass cube and glass spheres, whose inside
+    surfaces are what the rule is about."""
+    sc = pyscene.small_scene(seed=11, w=160, h=120, spp=4, depth=8, lights=lights, textures=True, glass=True)
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    ctx.set_light_sample_culling(0)
+    full = _buffers(ctx, sc)
+    c_full = ctx.counters()
+    assert int(c_full["shadowRaysSkipped"]) == 0
+    ctx.set_light_sample_culling(1)
+    culled = _buffers(ctx, sc)
+    c = ctx.counters()
+    for k in ("hit_ids", "hit_t", "depth", "sum", "albedo", "normal"):
+        a, b = full[k], culled[k]
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                              b.view(np.uint32) if b.dtype == np.float32 else b), k
+    assert int(c["shadowRaysSkipped"]) > 0
+    assert int(c["shadowRays"]) + int(c["shadowRaysSkipped"]) == int(c_full["shadowRays"])
+    assert int(c["extensionRays"]) == int(c_full["extensionRays"])
+    ctx.close()
