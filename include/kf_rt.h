@@ -260,8 +260,16 @@ KFRT_API int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTri
  * random number (PathTrace.rchit:107-108: a transmissive surface seen from inside), or any sample of a path
  * whose weight the BSDF has just taken to zero (rgen:119 ends it before its next draw) -- are answered without
  * a ray and counted in KfrtCounters.shadowRaysSkipped (on: 1, the default).  0 traces every light sample the
- * reference traces: same buffers bit for bit, shadowRays larger by exactly shadowRaysSkipped. */
+ * reference traces: same first-hit buffers bit for bit, radiance within the rounding of the shading arithmetic
+ * (the switch selects another instantiation of the shade kernel), shadowRays larger by shadowRaysSkipped. */
 KFRT_API int kfrtSetLightSampleCulling(KfrtContext* ctx, int on);
+/* kfrtBuildBlas finds out which geometries are convex (every vertex on or behind the plane of every triangle;
+ * closed convex meshes with outward winding, planar meshes, convex caps).  A bounce or occlusion ray that leaves
+ * such a geometry to the front side of the triangle it starts on, by more than a grazing margin, cannot meet it
+ * again, and the traversal stages do not enter the instance it starts on (on: 1, the default; environment
+ * override at kfrtCreate: KFRT_SKIP_OWN_INSTANCE).  0: every ray walks every instance its path meets, as in
+ * the reference; the buffers agree except where rounding makes a ray along its own convex surface hit it. */
+KFRT_API int kfrtSetOwnInstanceSkip(KfrtContext* ctx, int on);
 KFRT_API int kfrtGetBvhStats(KfrtContext* ctx, KfrtBvhStats* out);
 
 /* ------------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ struct BatchGeom {
   Node8* nodesAlloc;     // final storage: header record, then the nodes (set before the finishing kernels)
   Tri48* tris;
   ShadeTri* shade;
+  float4* faceNormal;    // object-space e1 x e2 per primitive
 };
 
 // Per-geometry state of the collapse, 8 words: [0] wide nodes allocated, [1] leaf primitives allocated,
@@ -275,6 +276,53 @@ __global__ void k_batch_write_shade_tris(const BatchGeom* __restrict__ geoms, co
   }
   t.matIndex = G.matIndex[prim];
   G.shade[prim] = t;
+  if (G.faceNormal) {
+    const float e1[3] = {b.pos[0] - a.pos[0], b.pos[1] - a.pos[1], b.pos[2] - a.pos[2]};
+    const float e2[3] = {c.pos[0] - a.pos[0], c.pos[1] - a.pos[1], c.pos[2] - a.pos[2]};
+    G.faceNormal[prim] = make_float4(e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                                     e1[0] * e2[1] - e1[1] * e2[0], 0.0f);
+  }
+}
+
+// Is the geometry convex, i.e. does every vertex lie on or behind the plane of every triangle (normal
+// e1 x e2)?  Then every triangle lies on the boundary of the convex hull of the mesh, and a ray that leaves a
+// point of the surface to the front side of its triangle cannot meet the mesh again -- what lets the
+// traversal stages skip the instance a bounce ray starts on (kf_trace.cuh, "skipInst").  Closed convex
+// meshes with outward winding qualify, and so do planar ones and convex caps.  grid.y = geometry, the
+// blocks of a geometry stride over its triangles; every thread walks all vertices (geometries whose
+// triangles x vertices exceed KF_CONVEX_MAX_WORK are not examined and count as not convex).  The tolerance,
+// 1e-5 of the geometry's extent, lets the two coplanar triangles of a quad pass.
+#define KF_CONVEX_MAX_WORK (uint64_t(1) << 28)
+__global__ void k_batch_convex(const BatchGeom* __restrict__ geoms, const int* __restrict__ sceneBoxes,
+                               uint32_t* __restrict__ convex) {
+  const uint32_t g = blockIdx.y;
+  const BatchGeom& G = geoms[g];
+  if (uint64_t(G.nTris) * G.nVerts > KF_CONVEX_MAX_WORK) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) convex[g] = 0u;
+    return;
+  }
+  const int* sb = sceneBoxes + 6 * g;
+  const float ext = fmaxf(orderedToFloat(sb[3]) - orderedToFloat(sb[0]),
+                          fmaxf(orderedToFloat(sb[4]) - orderedToFloat(sb[1]), orderedToFloat(sb[5]) - orderedToFloat(sb[2])));
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < G.nTris; t += gridDim.x * blockDim.x) {
+    const float* p0 = G.verts[G.idx[3 * t + 0]].pos;
+    const float* p1 = G.verts[G.idx[3 * t + 1]].pos;
+    const float* p2 = G.verts[G.idx[3 * t + 2]].pos;
+    const float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+    const float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+    const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+    const float tol = 1e-5f * ext * sqrtf(nx * nx + ny * ny + nz * nz);
+    bool ok = true;
+    for (uint32_t v = 0; v < G.nVerts && ok; v++) {
+      const float* q = G.verts[v].pos;
+      ok = nx * (q[0] - p0[0]) + ny * (q[1] - p0[1]) + nz * (q[2] - p0[2]) <= tol;
+      if ((v & 255u) == 255u && convex[g] == 0u) break;  // another triangle has already decided
+    }
+    if (!ok) {
+      convex[g] = 0u;
+      return;
+    }
+  }
 }
 
 }  // namespace kf

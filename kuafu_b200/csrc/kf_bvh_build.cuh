@@ -101,8 +101,9 @@ struct BlasInfo {
   const uint32_t* idx;
   const uint32_t* matIndex;
   const ShadeTri* shade;
+  const float4* faceNormal;  // object-space e1 x e2 per primitive
   float box[6];
-  uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque
+  uint32_t flags;  // bit0: usable (has triangles, not hidden); bit1: non-opaque; bit2: convex (k_batch_convex)
   uint32_t nVerts;
 };
 __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_t n,
@@ -143,7 +144,7 @@ __global__ void k_instance_setup(const KfrtInstance* __restrict__ insts, uint32_
   const bool usable = g < nBlas && (blas[g].flags & 1u);
   rec.verts = g < nBlas ? blas[g].verts : nullptr;
   rec.idx = g < nBlas ? blas[g].idx : nullptr;
-  rec.matIndex = g < nBlas ? blas[g].matIndex : nullptr;
+  rec.faceNormal = (g < nBlas && (blas[g].flags & 4u)) ? blas[g].faceNormal : nullptr;
   rec.shade = g < nBlas ? blas[g].shade : nullptr;
   recs[i] = rec;
   // the record the traversal reads, in the top-level node array

@@ -235,7 +235,7 @@ struct __align__(16) InstRec {
   float inv[12];            // world->object, 3 rows x 4 columns
   const KfrtVertex* verts;  // geometry tables (reference PathTrace.rchit:66-98)
   const uint32_t* idx;
-  const uint32_t* matIndex;
+  const float4* faceNormal;  // convex geometries only, else NULL: object-space geometric normal e1 x e2 of every primitive (see kf_blas_batch.cuh, k_batch_convex)
   const ShadeTri* shade;    // per-primitive shading records of the geometry
 };
 static_assert(sizeof(InstRec) == 80, "InstRec must be 80 bytes");

@@ -87,6 +87,8 @@ struct GeomHost {
   Node8* nodesAlloc = nullptr;  // nodesAlloc, tris and shade point into `block`
   Tri48* tris = nullptr;
   ShadeTri* shade = nullptr;
+  float4* faceNormal = nullptr;  // object-space e1 x e2 per primitive (in `block`)
+  bool convex = false;           // k_batch_convex: rays leaving its surface outwards skip the instance they start on
   std::shared_ptr<BlasBlock> block;
   uint32_t nNodes = 0;
   uint32_t depth = 0;  // levels of its wide tree
@@ -95,6 +97,7 @@ struct GeomHost {
     cudaFree(verts); cudaFree(idx); cudaFree(matIndex);
     block.reset();
     verts = nullptr; idx = nullptr; matIndex = nullptr; nodes = nullptr; nodesAlloc = nullptr; tris = nullptr; shade = nullptr;
+    faceNormal = nullptr; convex = false;
     present = false;
     nNodes = 0;
   }
@@ -120,7 +123,7 @@ struct BuildState {
   DevBuf<Node8> outNodes;
   // scratch of the batched bottom-level build (kf_blas_batch.cuh)
   DevBuf<BatchGeom> batchGeoms;
-  DevBuf<uint32_t> primGeom, batchCounters;
+  DevBuf<uint32_t> primGeom, batchCounters, batchConvex;
   DevBuf<int> batchBoxes;
   // scratch of the top-level SAH build (k_tlas_sah)
   DevBuf<uint32_t> sahSegOf, sahBinCount, sahPre, sahSegPre;
@@ -135,7 +138,7 @@ struct BuildState {
     valsB.release(); hist.release(); flags.release(); outPrim.release(); counters.release();
     children.release(); range.release(); parent.release(); wideBinary.release();
     wideMembers.release(); nodeBox.release(); outNodes.release(); slotOfInst.release();
-    batchGeoms.release(); primGeom.release(); batchCounters.release(); batchBoxes.release();
+    batchGeoms.release(); primGeom.release(); batchCounters.release(); batchBoxes.release(); batchConvex.release();
     sahSegOf.release(); sahBinCount.release(); sahPre.release(); sahSegPre.release(); sahSegs.release();
     sahDecision.release(); sahDecisionF.release(); sahBounds.release(); sahBinBox.release();
     sahBestKey.release();
@@ -196,6 +199,7 @@ struct KfrtContext {
   // world-space instance subtrees (kf_wsi.cuh): built lazily by the first kfrtRender after the instance
   // set or a transform has changed, when the instanced triangles fit the budget
   bool cullLightSamples = true;  // kfrtSetLightSampleCulling
+  bool skipOwnInstance = true;   // kfrtSetOwnInstanceSkip
   int wsiMode = 1;  // 0 never; 1 static scenes within the budget, if a timed probe says they are faster; 2 whenever they fit
   uint64_t wsiMaxTris = uint64_t(4) << 20;
   bool wsiValid = false, wsiDirty = true;
@@ -430,6 +434,7 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
     b.nodesAlloc = nullptr;
     b.tris = nullptr;
     b.shade = nullptr;
+    b.faceNormal = nullptr;
     nTris += b.nTris;
     nodeSlots += b.nTris + 1;
     maxTris = std::max(maxTris, b.nTris);
@@ -456,6 +461,17 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
   KF_CUDA(ctx, cudaMemcpyAsync(st.batchGeoms.p, table.data(), sizeof(BatchGeom) * count, cudaMemcpyHostToDevice, stream));
   k_batch_init<<<gridFor(6 * size_t(count), 256), 256, 0, stream>>>(st.batchBoxes.p, count);
   k_batch_tri_boxes<<<gridFor(n, 256), 256, 0, stream>>>(st.batchGeoms.p, count, n, st.primBox.p, st.primGeom.p, st.batchBoxes.p);
+  // which geometries are convex (their answer comes back with the node counts below)
+  std::vector<uint32_t> convex(count, 1u);
+  KF_CUDA(ctx, st.batchConvex.ensure(count));
+  KF_CUDA(ctx, cudaMemcpyAsync(st.batchConvex.p, convex.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream));
+  {
+    uint32_t maxExamined = 1;
+    for (uint32_t i = 0; i < count; i++)
+      if (uint64_t(table[i].nTris) * table[i].nVerts <= KF_CONVEX_MAX_WORK) maxExamined = std::max(maxExamined, table[i].nTris);
+    const unsigned cx = std::max(1u, std::min<unsigned>(gridFor(maxExamined, 128), std::max(1u, unsigned(ctx->numSMs) * 16u / count)));
+    k_batch_convex<<<dim3(cx, count), 128, 0, stream>>>(st.batchGeoms.p, st.batchBoxes.p, st.batchConvex.p);
+  }
   if (n > 1) {
     k_batch_morton<<<gridFor(n, 256), 256, 0, stream>>>(st.primBox.p, st.primGeom.p, n, st.batchBoxes.p, st.keysA.p, st.valsA.p);
     int geomBits = 0;
@@ -501,6 +517,7 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
     }
     KF_CUDA(ctx, cudaMemcpyAsync(counters.data(), st.batchCounters.p, sizeof(uint32_t) * counters.size(), cudaMemcpyDeviceToHost, stream));
     KF_CUDA(ctx, cudaMemcpyAsync(boxes.data(), st.batchBoxes.p, sizeof(int) * boxes.size(), cudaMemcpyDeviceToHost, stream));
+    KF_CUDA(ctx, cudaMemcpyAsync(convex.data(), st.batchConvex.p, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, stream));
     KF_CUDA(ctx, cudaStreamSynchronize(stream));
     done = true;
     for (uint32_t i = 0; i < count; i++) {
@@ -513,12 +530,13 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
   // final storage: one allocation for the batch, 256-byte aligned pieces
   auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
   size_t bytes = 0;
-  std::vector<size_t> offNodes(count), offTris(count), offShade(count);
+  std::vector<size_t> offNodes(count), offTris(count), offShade(count), offNormal(count);
   for (uint32_t i = 0; i < count; i++) {
     const uint32_t nWide = counters[size_t(KF_BATCH_COUNTERS) * i];
     offNodes[i] = bytes; bytes = align(bytes + sizeof(Node8) * (size_t(nWide) + 1));
     offTris[i] = bytes; bytes = align(bytes + sizeof(Tri48) * table[i].nTris);
     offShade[i] = bytes; bytes = align(bytes + sizeof(ShadeTri) * table[i].nTris);
+    offNormal[i] = bytes; bytes = align(bytes + sizeof(float4) * table[i].nTris);
   }
   auto block = std::make_shared<BlasBlock>();
   block->stream = stream;
@@ -531,12 +549,15 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
     g.nodes = g.nodesAlloc + 1;
     g.tris = reinterpret_cast<Tri48*>(base + offTris[i]);
     g.shade = reinterpret_cast<ShadeTri*>(base + offShade[i]);
+    g.faceNormal = reinterpret_cast<float4*>(base + offNormal[i]);
+    g.convex = convex[i] != 0u;
     g.nNodes = counters[size_t(KF_BATCH_COUNTERS) * i];
     g.depth = counters[size_t(KF_BATCH_COUNTERS) * i + 4];
     orderedBoxToFloat(&boxes[size_t(6) * i], g.box);
     table[i].nodesAlloc = g.nodesAlloc;
     table[i].tris = g.tris;
     table[i].shade = g.shade;
+    table[i].faceNormal = g.faceNormal;
     KF_CUDA(ctx, cudaMemsetAsync(g.nodesAlloc, 0, sizeof(Node8), stream));  // the header record
   }
   KF_CUDA(ctx, cudaMemcpyAsync(st.batchGeoms.p, table.data(), sizeof(BatchGeom) * count, cudaMemcpyHostToDevice, stream));
@@ -570,9 +591,10 @@ static int uploadTables(KfrtContext* ctx) {
     infos[i].idx = g.idx;
     infos[i].matIndex = g.matIndex;
     infos[i].shade = g.shade;
+    infos[i].faceNormal = g.faceNormal;
     infos[i].nVerts = g.nVerts;
     std::memcpy(infos[i].box, g.box, sizeof(g.box));
-    infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u);
+    infos[i].flags = ((g.present && g.nodes != nullptr) ? 1u : 0u) | (g.opaque ? 0u : 2u) | (g.convex ? 4u : 0u);
   }
   KF_CUDA(ctx, ctx->geomTable.ensure(recs.size()));
   KF_CUDA(ctx, ctx->blasInfo.ensure(infos.size()));
@@ -706,6 +728,7 @@ int kfrtCreate(int deviceOrdinal, KfrtContext** out) {
     }
   }
   if (const char* e = std::getenv("KFRT_TRACE_LOG")) ctx->traceLog = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KFRT_SKIP_OWN_INSTANCE")) ctx->skipOwnInstance = std::atoi(e) != 0;
   if (const char* e = std::getenv("KFRT_INSTANCE_SUBTREES")) ctx->wsiMode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("KFRT_INSTANCE_SUBTREES_MAX_TRIS")) {
     const long long v = std::atoll(e);
@@ -954,6 +977,8 @@ int kfrtBuildBlas(KfrtContext* ctx) {
     g.nodesAlloc = nullptr;
     g.tris = nullptr;
     g.shade = nullptr;
+    g.faceNormal = nullptr;
+    g.convex = false;
     g.nNodes = 0;
     g.depth = 0;
     g.dirty = false;
@@ -1383,6 +1408,12 @@ int kfrtSetLightSampleCulling(KfrtContext* ctx, int on) {
   return KFRT_OK;
 }
 
+int kfrtSetOwnInstanceSkip(KfrtContext* ctx, int on) {
+  KF_CHECK_CTX(ctx);
+  ctx->skipOwnInstance = on != 0;
+  return KFRT_OK;
+}
+
 int kfrtSetInstanceSubtrees(KfrtContext* ctx, int mode, uint64_t maxTriangles) {
   KF_CHECK_CTX(ctx);
   if (mode < 0 || mode > 2) KF_FAIL(ctx, KFRT_ERR_INVALID, "instance-subtree mode must be 0, 1 or 2");
@@ -1459,6 +1490,41 @@ static void launchTrace(KfrtContext* ctx, const TraceArgs& te, bool any, bool de
   }
 }
 
+// Shade and shadow-resolve launches: variant = MULTI << 1 | DETAIL (the grid table's index); the culling of light
+// samples and the own-instance skip are template parameters of the kernels (kf_wavefront.cuh).
+template <bool MULTI, bool DETAIL>
+static void launchShadeVariant(KfrtContext* ctx, int grid, const WfArgs& a, int q, uint32_t depth) {
+  cudaStream_t st = ctx->stream;
+  const int sel = (ctx->cullLightSamples ? 2 : 0) | (ctx->skipOwnInstance ? 1 : 0);
+  switch (sel) {
+    case 0: k_wf_shade<MULTI, DETAIL, false, false><<<grid, KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+    case 1: k_wf_shade<MULTI, DETAIL, false, true><<<grid, KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+    case 2: k_wf_shade<MULTI, DETAIL, true, false><<<grid, KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+    default: k_wf_shade<MULTI, DETAIL, true, true><<<grid, KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
+  }
+}
+static void launchShade(KfrtContext* ctx, int variant, const WfArgs& a, int q, uint32_t depth) {
+  switch (variant) {
+    case 0: launchShadeVariant<false, false>(ctx, ctx->gridShade[0], a, q, depth); break;
+    case 1: launchShadeVariant<false, true>(ctx, ctx->gridShade[1], a, q, depth); break;
+    case 2: launchShadeVariant<true, false>(ctx, ctx->gridShade[2], a, q, depth); break;
+    default: launchShadeVariant<true, true>(ctx, ctx->gridShade[3], a, q, depth); break;
+  }
+}
+template <bool MULTI, bool DETAIL>
+static void launchShadowResolveVariant(KfrtContext* ctx, int grid, const WfArgs& a, int sq, int qNext, uint32_t depth) {
+  if (ctx->cullLightSamples) k_wf_shadow_resolve<MULTI, DETAIL, true><<<grid, 128, 0, ctx->stream>>>(a, sq, qNext, depth);
+  else k_wf_shadow_resolve<MULTI, DETAIL, false><<<grid, 128, 0, ctx->stream>>>(a, sq, qNext, depth);
+}
+static void launchShadowResolve(KfrtContext* ctx, int variant, const WfArgs& a, int sq, int qNext, uint32_t depth) {
+  switch (variant) {
+    case 0: launchShadowResolveVariant<false, false>(ctx, ctx->gridShadow[0], a, sq, qNext, depth); break;
+    case 1: launchShadowResolveVariant<false, true>(ctx, ctx->gridShadow[1], a, sq, qNext, depth); break;
+    case 2: launchShadowResolveVariant<true, false>(ctx, ctx->gridShadow[2], a, sq, qNext, depth); break;
+    default: launchShadowResolveVariant<true, true>(ctx, ctx->gridShadow[3], a, sq, qNext, depth); break;
+  }
+}
+
 // Path-state buffers of the wavefront scheduler for `slots` path slots (they only ever grow).
 static int ensurePathState(KfrtContext* ctx, size_t slots, bool multi) {
   if (slots >= (size_t(1) << 31)) KF_FAIL(ctx, KFRT_ERR_INVALID, "too many pixels for one batch");
@@ -1504,14 +1570,15 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
     ctx->gridTraceWsi[1] = persistentGrid(ctx, k_wf_trace_wsi<false, true>, 128);
     ctx->gridTraceWsi[2] = persistentGrid(ctx, k_wf_trace_wsi<true, false>, 128);
     ctx->gridTraceWsi[3] = persistentGrid(ctx, k_wf_trace_wsi<true, true>, 128);
-    ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false>, KF_SHADE_THREADS);
-    ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true>, KF_SHADE_THREADS);
-    ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false>, KF_SHADE_THREADS);
-    ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true>, KF_SHADE_THREADS);
-    ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow_resolve<false, false>, 128);
-    ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow_resolve<false, true>, 128);
-    ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow_resolve<true, false>, 128);
-    ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow_resolve<true, true>, 128);
+    // (sized for the default variants; the others share their launch bounds)
+    ctx->gridShade[0] = persistentGrid(ctx, k_wf_shade<false, false, true, true>, KF_SHADE_THREADS);
+    ctx->gridShade[1] = persistentGrid(ctx, k_wf_shade<false, true, true, true>, KF_SHADE_THREADS);
+    ctx->gridShade[2] = persistentGrid(ctx, k_wf_shade<true, false, true, true>, KF_SHADE_THREADS);
+    ctx->gridShade[3] = persistentGrid(ctx, k_wf_shade<true, true, true, true>, KF_SHADE_THREADS);
+    ctx->gridShadow[0] = persistentGrid(ctx, k_wf_shadow_resolve<false, false, true>, 128);
+    ctx->gridShadow[1] = persistentGrid(ctx, k_wf_shadow_resolve<false, true, true>, 128);
+    ctx->gridShadow[2] = persistentGrid(ctx, k_wf_shadow_resolve<true, false, true>, 128);
+    ctx->gridShadow[3] = persistentGrid(ctx, k_wf_shadow_resolve<true, true, true>, 128);
   }
 
   WfArgs a;
@@ -1538,7 +1605,6 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
   a.tilesY = tilesY;
   a.slotsPerSample = uint32_t(slotsPerSample);
   a.firstSample = ra.s0;
-  a.cullLightSamples = ctx->cullLightSamples ? 1u : 0u;
   a.pc = ra.pc;
   a.clockBase = ra.clockBase;
   a.sum = ra.sum;
@@ -1598,12 +1664,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
       launchTrace(ctx, te, false, d != 0);
       logEnd("closest", depth, te.count);
       stageMark(ctx, KFRT_STAGE_SHADE);
-      switch (variant) {
-        case 0: k_wf_shade<false, false><<<ctx->gridShade[0], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
-        case 1: k_wf_shade<false, true><<<ctx->gridShade[1], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
-        case 2: k_wf_shade<true, false><<<ctx->gridShade[2], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
-        default: k_wf_shade<true, true><<<ctx->gridShade[3], KF_SHADE_THREADS, 0, st>>>(a, q, depth); break;
-      }
+      launchShade(ctx, variant, a, q, depth);
       ctx->launches += 2;
       const uint32_t rounds = ctx->nLightSlots;
       for (uint32_t l = 0; l < rounds; l++) {
@@ -1621,12 +1682,7 @@ static int renderWavefront(KfrtContext* ctx, const RenderArgs& ra) {
         launchTrace(ctx, ts, true, d != 0);
         logEnd("occlusion", depth, ts.count);
         stageMark(ctx, KFRT_STAGE_SHADOW_RESOLVE);
-        switch (variant) {
-          case 0: k_wf_shadow_resolve<false, false><<<ctx->gridShadow[0], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          case 1: k_wf_shadow_resolve<false, true><<<ctx->gridShadow[1], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          case 2: k_wf_shadow_resolve<true, false><<<ctx->gridShadow[2], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-          default: k_wf_shadow_resolve<true, true><<<ctx->gridShadow[3], 128, 0, st>>>(a, sq, q ^ 1, depth); break;
-        }
+        launchShadowResolve(ctx, variant, a, sq, q ^ 1, depth);
         ctx->launches += 2;
         if (multi && l + 1 < rounds) {
           stageMark(ctx, KFRT_STAGE_OTHER);

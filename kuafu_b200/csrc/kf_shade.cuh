@@ -186,8 +186,14 @@ KF_D V3 shadeMiss(const SceneDev& sc, const KfrtPushConstants& pc, V3 dir, uint3
 // reference PathTrace.rchit:66-98 + :322-455.  Returns false when the hit is emissive (path ends,
 // `emission` valid); otherwise fills the surface context, the sampled direction L, the BSDF weight
 // and the first-hit albedo.
+// ngOut (shared memory, stride ngStride floats; may be NULL): receives the geometric normal e1 x e2 of the hit
+// triangle of a CONVEX geometry, taken to world space like a shading normal (M^-T n, so that dot(Ng, d) has
+// the sign of the object-space normal . M^-1 d), or zero for other geometries -- written here, where the
+// rows of the inverse are in registers anyway, and read back by the caller once the outgoing directions are
+// known (kept in registers across the BSDF code it costs the kernel spills).
 KF_D bool shadeSurface(const SceneDev& sc, const Hit& h, V3 rayO, V3 rayD, uint32_t& seed, Surface& sf,
-                       V3& L, V3& weight, V3& albedo, V3& emission, uint32_t& texFetches) {
+                       V3& L, V3& weight, V3& albedo, V3& emission, uint32_t& texFetches,
+                       float* ngOut = nullptr, uint32_t ngStride = 0) {
   const float4* ip = reinterpret_cast<const float4*>(sc.inst + h.inst);
   const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
   const ulonglong2 p23 = __ldg(reinterpret_cast<const ulonglong2*>(ip + 4));
@@ -203,6 +209,18 @@ KF_D bool shadeSurface(const SceneDev& sc, const Hit& h, V3 rayO, V3 rayD, uint3
   wn.y = (ln.x * r0.y + ln.y * r1.y) + ln.z * r2.y;
   wn.z = (ln.x * r0.z + ln.y * r1.z) + ln.z * r2.z;
   V3 N = normalize(wn);
+  if (ngOut) {
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    if (p23.x != 0ull) {
+      const float4 gn = __ldg(reinterpret_cast<const float4*>(p23.x) + h.prim);
+      gx = (gn.x * r0.x + gn.y * r1.x) + gn.z * r2.x;
+      gy = (gn.x * r0.y + gn.y * r1.y) + gn.z * r2.y;
+      gz = (gn.x * r0.z + gn.y * r1.z) + gn.z * r2.z;
+    }
+    ngOut[0] = gx;
+    ngOut[ngStride] = gy;
+    ngOut[2 * ngStride] = gz;
+  }
   const V3 worldPos = rayO + rayD * h.t;
   const float uvx = (s2.y * bx + s2.w * by) + s3.y * bz;
   const float uvy = (s2.z * bx + s3.x * by) + s3.z * bz;

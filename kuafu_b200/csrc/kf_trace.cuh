@@ -88,6 +88,12 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
   // less per lane.
   __shared__ float sWorld[10][128];
   __shared__ MaskTables sMask;
+  // The instance the lane's ray must not enter, or ~0: a bounce ray that leaves a convex geometry to the
+  // front side of the triangle it starts on cannot meet that geometry again (k_batch_convex), and the shade
+  // stage says so in the spare word of the ray's origin.  Without it every such ray walks the bottom
+  // level of its own surface around its origin, finds the triangle it stands on and its neighbours, and
+  // rejects them all.
+  __shared__ uint32_t sSkip[128];
   fillMaskTables(sMask);
   __syncthreads();
   const uint32_t tid = threadIdx.x;
@@ -162,6 +168,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
             hit.inst = -1;
             hit.prim = -1;
             hit.front = 0;
+            {
+              const uint32_t ob = __float_as_uint(o4.w);
+              sSkip[tid] = ((ob >> (ANY ? 31 : 30)) & 1u) ? (ob & 0x1fffffffu) : 0xffffffffu;
+            }
             r = setupRay(o, d);
             // the world-space setup is parked once per ray; popGroup() restores it on every return
             sWorld[0][tid] = r.ox; sWorld[1][tid] = r.oy; sWorld[2][tid] = r.oz;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace(TraceArgs a) {
         const float t0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), tmin));
         const float t1 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), hit.t));
         const ulonglong2 ptrs = __ldg(reinterpret_cast<const ulonglong2*>(ip + 3));
-        if (t0 <= t1 && ptrs.x != 0ull) {
+        if (t0 <= t1 && ptrs.x != 0ull && w4.w != sSkip[tid]) {
           const float4 r0 = __ldg(reinterpret_cast<const float4*>(ip) + 0);
           const float4 r1 = __ldg(reinterpret_cast<const float4*>(ip) + 1);
           const float4 r2 = __ldg(reinterpret_cast<const float4*>(ip) + 2);

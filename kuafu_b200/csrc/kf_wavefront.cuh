@@ -60,7 +60,6 @@ struct WfArgs {
   uint32_t slotsPerSample;               // nCams * tilesX * tilesY * 32
   uint32_t batchBegin, batchCount;       // global sample index of the first sample, samples in batch
   uint32_t firstSample;                  // sampleBegin of the kfrtRender call
-  uint32_t cullLightSamples;             // 1: light samples whose occlusion ray cannot matter are not traced (nextRelevantLight)
   KfrtPushConstants pc;
   uint32_t clockBase;
   float4* sum;
@@ -147,6 +146,15 @@ __global__ void __launch_bounds__(256) k_wf_raygen(WfArgs a) {
 // same whether its ray is occluded or not, so the ray is not traced: 21 % of the occlusion rays of config 3,
 // whose glass spheres are lit from inside by every path that crosses them.  Such rays are counted in
 // counters[11] (KfrtCounters.shadowRaysSkipped), not in shadowRays.
+// A ray that leaves a convex geometry to the front side of the triangle it starts on cannot meet that
+// geometry again (k_batch_convex): the traversal stages skip the instance it starts on.  The test keeps a
+// margin (sine of the elevation above the triangle's plane > 1e-3): a grazing ray takes the full walk, so that
+// what rounding makes of a ray along its own surface stays what the oracle makes of it.  Ng: M^-T (e1 x e2).
+KF_D bool leavesSurface(V3 Ng, V3 d) {
+  const float s = dot(Ng, d);
+  return s > 0.0f && s * s > 1e-6f * dot(Ng, Ng) * dot(d, d);
+}
+
 KF_D bool nextRelevantLight(const SceneDev& sc, const Surface& sf, uint32_t& seed, int& k, V3& L, float& maxDist,
                             V3& lightEmission, uint32_t& texFetches, V3& contrib, uint32_t& specSeed, uint32_t& skipped,
                             bool cull) {
@@ -183,7 +191,10 @@ KF_D void loadCtx(const float4* __restrict__ c, Surface& sf, int& k, V3& acc) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool DETAIL>
+// CULL: light samples whose occlusion ray cannot matter are not traced (nextRelevantLight); OWN: rays that
+// leave a convex geometry outwards skip the instance they start on (leavesSurface).  Both are the product's
+// defaults; they are template parameters because as run-time flags they cost the stage 6 % and 4 %.
+template <bool MULTI, bool DETAIL, bool CULL, bool OWN>
 __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_shade(WfArgs a, int q, uint32_t depth) {
   const uint32_t count = a.b.counts[q];
   const uint32_t* __restrict__ queue = a.b.queue[q];
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
   __shared__ uint32_t sQposBuf[2][KF_SHADE_THREADS];
   __shared__ int sHitBuf[2][KF_SHADE_THREADS];
   __shared__ uint32_t sClassBuf[2][2][WARPS];  // per warp: hits, misses
+  __shared__ float sNg[3][KF_SHADE_THREADS];    // geometric normal of a convex geometry's hit, until its light is chosen
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t round = 0;
   // The queue entry and hit record of the NEXT round are fetched while this round is shaded: the deal
@@ -331,7 +343,8 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
         }
         Surface sf;
         V3 L, w, albedo, emission;
-        if (!shadeSurface(a.sc, hit, ro, rd, seed, sf, L, w, albedo, emission, tex)) {
+        if (!shadeSurface(a.sc, hit, ro, rd, seed, sf, L, w, albedo, emission, tex,
+                          OWN ? &sNg[0][threadIdx.x] : nullptr, KF_SHADE_THREADS)) {
           addColor(emission * weight);  // emissive surface ends the path (rchit:330-334)
           if (firstHitOutputs) {
             a.albedo[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -345,20 +358,37 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           if (!finite3(weight)) addColor(mk3(0.0f) * weight);  // ray.emission = 0 (rgen:109 keeps NaN/Inf semantics)
           weight *= w;                  // rgen:110; the NEE sum is scaled by the post-BSDF weight
           // next extension ray (rchit:462-463); the occlusion rays share its origin
-          a.b.rayO[slot] = make_float4(sf.worldPos.x, sf.worldPos.y, sf.worldPos.z, 0.0f);
+          // A ray that leaves a convex geometry to the front side of the triangle it starts on cannot meet that
+          // geometry again (k_batch_convex): the traversal stages skip the instance it starts on.  The test
+          // keeps a margin (sine of the elevation > 1e-3): a grazing ray takes the full walk, so that what
+          // rounding makes of a ray along its own surface stays what the oracle makes of it.
+          // instance | convex << 29 | extension ray skips it << 30 | occlusion ray skips it << 31
+          uint32_t originBits = 0u;
+          if (OWN) {
+            // (the instance is read again from where the deal left it, the normal from where shadeSurface left it)
+            const V3 Ng = mk3(sNg[0][threadIdx.x], sNg[1][threadIdx.x], sNg[2][threadIdx.x]);
+            const uint32_t oInst = uint32_t(sHitB[threadIdx.x]) & 0x7fffffffu;
+            if ((Ng.x != 0.0f || Ng.y != 0.0f || Ng.z != 0.0f) && oInst < (1u << 29))
+              originBits = oInst | (1u << 29) | (leavesSurface(Ng, L) ? 1u << 30 : 0u);
+          }
           a.b.rayD[slot] = make_float4(L.x, L.y, L.z, 0.0f);
           int k = 0;
           V3 Ls, le, contrib = mk3(0.0f);
           float maxDist;
           uint32_t specSeed = seed;
-          bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, a.cullLightSamples != 0u);
+          bool need = nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, CULL);
           // A path whose weight the BSDF sample has just taken to exactly zero (a GGX direction below the
           // horizon, rchit:420-428) adds `shadow_color * 0` and then ends before its next random draw
           // (rgen:119): its light sample cannot matter either, unless the contribution is not finite.
-          if (!MULTI && need && a.cullLightSamples && allEq(weight, mk3(0.0f)) && finite3(contrib)) {
+          if (!MULTI && CULL && need && allEq(weight, mk3(0.0f)) && finite3(contrib)) {
             need = false;
             skipTotal++;
           }
+          if (!MULTI && need && originBits &&
+              leavesSurface(mk3(sNg[0][threadIdx.x], sNg[1][threadIdx.x], sNg[2][threadIdx.x]), Ls))
+            originBits |= 1u << 31;
+          originBits = (originBits >> 30) ? (originBits & ~(1u << 29)) : 0u;  // the spare word of the origin
+          a.b.rayO[slot] = make_float4(sf.worldPos.x, sf.worldPos.y, sf.worldPos.z, __uint_as_float(originBits));
           if (need) {
             a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
             a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
@@ -389,7 +419,7 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
 
 // ---------------------------------------------------------------------------------------------
 // sq: which shadow queue to read; q: the extension queue being filled for the next bounce.
-template <bool MULTI, bool DETAIL>
+template <bool MULTI, bool DETAIL, bool CULL>
 __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int qNext, uint32_t depth) {
   const uint32_t count = a.b.counts[2 + sq];
   const uint32_t* __restrict__ queue = a.b.shadowQueue[sq];
@@ -446,7 +476,7 @@ __global__ void __launch_bounds__(128) k_wf_shadow_resolve(WfArgs a, int sq, int
         uint32_t tex = 0;
         V3 contrib = mk3(0.0f);
         uint32_t specSeed = seed;
-        if (nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, a.cullLightSamples != 0u)) {
+        if (nextRelevantLight(a.sc, sf, seed, k, Ls, maxDist, le, tex, contrib, specSeed, skipTotal, CULL)) {
           a.b.shadowL[slot] = make_float4(Ls.x, Ls.y, Ls.z, maxDist);
           a.b.shadowC[slot] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(specSeed));
           storeCtx(a.b.ctx + size_t(6) * slot, sf, k, acc);

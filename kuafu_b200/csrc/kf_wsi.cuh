@@ -68,14 +68,14 @@ __global__ void k_wsi_world_verts(const WsiInst* __restrict__ vis, const KfrtIns
 
 // grid.y = visible instance: its subtree from the build scratch to its final place.  Node 0 goes into the
 // instance's slot of the top-level array, nodes 1.. to [nodeStart, ...); child and triangle indices become
-// absolute, and every node is stamped with instance | non-opaque << 31.
+// absolute, and every node is stamped with (instance + 1) | non-opaque << 31.
 __global__ void k_wsi_place_nodes(const WsiInst* __restrict__ vis, const BatchGeom* __restrict__ geoms,
                                   const uint32_t* __restrict__ counters, const Node8* __restrict__ scratch,
                                   const uint32_t* __restrict__ slotOfInst, Node8* __restrict__ nodes) {
   const WsiInst V = vis[blockIdx.y];
   const BatchGeom& G = geoms[blockIdx.y];
   const uint32_t nWide = counters[KF_BATCH_COUNTERS * blockIdx.y];
-  const uint32_t stamp = V.instance | ((V.flags & 2u) ? 0x80000000u : 0u);
+  const uint32_t stamp = (V.instance + 1u) | ((V.flags & 2u) ? 0x80000000u : 0u);  // (top-level nodes carry 0)
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nWide; j += gridDim.x * blockDim.x) {
     Node8 nd = scratch[G.nodeOffset + j];
     nd.childBase = V.nodeStart + nd.childBase - 1u;  // relative index c >= 1 -> nodeStart + c - 1
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace_wsi(TraceArgs a) 
   uint32_t qpos = 0;
   RaySetup r = setupRay(mk3(0.0f), mk3(1.0f));  // the world-space ray, for the whole walk
   V3 oo = mk3(0.0f), od = mk3(1.0f);            // the ray in the object space of instance `curInst`
-  uint32_t curInst = 0xffffffffu;               // instance | non-opaque << 31, as stamped on the nodes
+  uint32_t curInst = 0xffffffffu;               // (instance + 1) | non-opaque << 31, as stamped on the nodes
+  uint32_t skipStamp = 0xffffffffu;
   __shared__ MaskTables sMask;
   fillMaskTables(sMask);
   __syncthreads();
@@ -187,6 +188,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace_wsi(TraceArgs a) 
             hit.prim = -1;
             hit.front = 0;
             r = setupRay(mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+            {
+              const uint32_t ob = __float_as_uint(o4.w);  // the instance the ray must not enter (kf_trace.cuh, sSkip), as a stamp
+              skipStamp = ((ob >> (ANY ? 31 : 30)) & 1u) ? (ob & 0x1fffffffu) + 1u : 0xffffffffu;
+            }
             curInst = 0xffffffffu;
             sp = 0;
             ng = make_uint2(0u, nodes ? 0x80000000u : 0u);  // the root: "child 7 ^ octinv of a virtual parent"
@@ -211,8 +216,10 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace_wsi(TraceArgs a) 
       const uint4* q = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
       const uint4 n0 = __ldg(q + 0), n1 = __ldg(q + 1), n2 = __ldg(q + 2), n3 = __ldg(q + 3), n4 = __ldg(q + 4);
       uint32_t childBase, primBase, imask, triMask;
-      const uint32_t miss = intersectNodeWords(n0, n1, n2, n3, n4, r, tmin, hit.t, childBase, primBase, imask, triMask);
+      const uint32_t miss0 = intersectNodeWords(n0, n1, n2, n3, n4, r, tmin, hit.t, childBase, primBase, imask, triMask);
       if (DETAIL) tc.nodes++;
+      uint32_t miss = miss0;
+      if ((n1.w & 0x7fffffffu) == skipStamp) miss = 0xffu;  // a node of the subtree the ray starts on and leaves
       const uint32_t inner = sMask.perm[r.octinv][imask & ~miss];
       ng = make_uint2(childBase, (inner << 24) | imask);
       tg = make_uint2(primBase, (uint32_t(sMask.expand[miss]) | 0xffff0000u) & triMask);
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace_wsi(TraceArgs a) 
       const uint32_t iw = tgInst;
       if (iw != curInst) {
         // world -> object (fused arithmetic, the same expressions as oracle traceInstance())
-        const float4* ip = reinterpret_cast<const float4*>(sc.inst + (iw & 0x7fffffffu));
+        const float4* ip = reinterpret_cast<const float4*>(sc.inst + ((iw & 0x7fffffffu) - 1u));
         const float4 r0 = __ldg(ip + 0), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2);
         if (DETAIL) tc.insts++;
         oo.x = cfma(r0.z, r.oz, cfma(r0.y, r.oy, cfma(r0.x, r.ox, r0.w)));
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(128, ANY ? 8 : 7) k_wf_trace_wsi(TraceArgs a) 
         od.z = cfma(r2.z, r.dz, cfma(r2.y, r.dy, cmul(r2.x, r.dx)));
         curInst = iw;
       }
-      const int32_t inst = int32_t(iw & 0x7fffffffu);
+      const int32_t inst = int32_t((iw & 0x7fffffffu) - 1u);
       // Moller-Trumbore, fused arithmetic, same expressions as oracle intersectTri()
       const V3 E1 = mk3(e1.x, e1.y, e1.z), E2 = mk3(e2.x, e2.y, e2.z);
       const V3 pv = fcross(od, E2);

@@ -39,7 +39,7 @@ def load():
         "kfrtSetEnvironmentCube": [vp, C.POINTER(vp), u32], "kfrtClearEnvironment": [vp],
         "kfrtSetLights": [vp, vp, vp, vp], "kfrtBuildBlas": [vp], "kfrtSetInstances": [vp, vp, u32],
         "kfrtBuildTlas": [vp], "kfrtRefitTlas": [vp, vp, u32], "kfrtGetBvhStats": [vp, vp],
-        "kfrtSetInstanceSubtrees": [vp, i32, C.c_uint64], "kfrtSetLightSampleCulling": [vp, i32],
+        "kfrtSetInstanceSubtrees": [vp, i32, C.c_uint64], "kfrtSetLightSampleCulling": [vp, i32], "kfrtSetOwnInstanceSkip": [vp, i32],
         "kfrtRender": [vp, vp, u32, u32, u32, vp, u32, u32, u32], "kfrtResolve": [vp],
         "kfrtReduceNccl": [vp, vp, i32], "kfrtDownloadBGRA8": [vp, u32, vp, sz],
         "kfrtMapBGRA8": [vp, u32, C.POINTER(vp), C.POINTER(sz)],
@@ -178,6 +178,9 @@ class Context:
 
     def set_light_sample_culling(self, on):
         self._ck(self.lib.kfrtSetLightSampleCulling(self.h, int(on)))
+
+    def set_own_instance_skip(self, on):
+        self._ck(self.lib.kfrtSetOwnInstanceSkip(self.h, int(on)))
 
     def bvh_stats(self):
         s = np.zeros((), wire.BVH_STATS)
