@@ -289,18 +289,18 @@ __global__ void k_batch_write_shade_tris(const BatchGeom* __restrict__ geoms, co
 // point of the surface to the front side of its triangle cannot meet the mesh again -- what lets the
 // traversal stages skip the instance a bounce ray starts on (kf_trace.cuh, "skipInst").  Closed convex
 // meshes with outward winding qualify, and so do planar ones and convex caps.  grid.y = geometry, the
-// blocks of a geometry stride over its triangles; every thread walks all vertices (geometries whose
-// triangles x vertices exceed KF_CONVEX_MAX_WORK are not examined and count as not convex).  The tolerance,
+// blocks of a geometry stride over its triangles; every thread walks all vertices.  Geometries whose
+// triangles x vertices exceed KF_CONVEX_MAX_WORK, and those that come after a batch has spent
+// KF_CONVEX_BATCH_WORK on the ones before them, are not examined and count as not convex: the host enters
+// them with convex[g] = 0.  The tolerance,
 // 1e-5 of the geometry's extent, lets the two coplanar triangles of a quad pass.
 #define KF_CONVEX_MAX_WORK (uint64_t(1) << 28)
+#define KF_CONVEX_BATCH_WORK (uint64_t(1) << 33)  // ~40 ms of a B200 in the worst case (no early exit: all of them convex)
 __global__ void k_batch_convex(const BatchGeom* __restrict__ geoms, const int* __restrict__ sceneBoxes,
                                uint32_t* __restrict__ convex) {
   const uint32_t g = blockIdx.y;
   const BatchGeom& G = geoms[g];
-  if (uint64_t(G.nTris) * G.nVerts > KF_CONVEX_MAX_WORK) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) convex[g] = 0u;
-    return;
-  }
+  if (convex[g] == 0u) return;  // not examined: too large, or the batch's budget is spent (the host says so)
   const int* sb = sceneBoxes + 6 * g;
   const float ext = fmaxf(orderedToFloat(sb[3]) - orderedToFloat(sb[0]),
                           fmaxf(orderedToFloat(sb[4]) - orderedToFloat(sb[1]), orderedToFloat(sb[5]) - orderedToFloat(sb[2])));

@@ -464,11 +464,19 @@ static int buildBlasBatch(KfrtContext* ctx, GeomHost* const* list, uint32_t coun
   // which geometries are convex (their answer comes back with the node counts below)
   std::vector<uint32_t> convex(count, 1u);
   KF_CUDA(ctx, st.batchConvex.ensure(count));
-  KF_CUDA(ctx, cudaMemcpyAsync(st.batchConvex.p, convex.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream));
   {
     uint32_t maxExamined = 1;
-    for (uint32_t i = 0; i < count; i++)
-      if (uint64_t(table[i].nTris) * table[i].nVerts <= KF_CONVEX_MAX_WORK) maxExamined = std::max(maxExamined, table[i].nTris);
+    uint64_t spent = 0;
+    for (uint32_t i = 0; i < count; i++) {
+      const uint64_t work = uint64_t(table[i].nTris) * table[i].nVerts;
+      if (work <= KF_CONVEX_MAX_WORK && spent + work <= KF_CONVEX_BATCH_WORK) {
+        spent += work;
+        maxExamined = std::max(maxExamined, table[i].nTris);
+      } else {
+        convex[i] = 0u;  // not examined
+      }
+    }
+    KF_CUDA(ctx, cudaMemcpyAsync(st.batchConvex.p, convex.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, stream));
     const unsigned cx = std::max(1u, std::min<unsigned>(gridFor(maxExamined, 128), std::max(1u, unsigned(ctx->numSMs) * 16u / count)));
     k_batch_convex<<<dim3(cx, count), 128, 0, stream>>>(st.batchGeoms.p, st.batchBoxes.p, st.batchConvex.p);
   }
