@@ -357,11 +357,8 @@ __global__ void __launch_bounds__(KF_SHADE_THREADS, KF_SHADE_MIN_BLOCKS) k_wf_sh
           }
           if (!finite3(weight)) addColor(mk3(0.0f) * weight);  // ray.emission = 0 (rgen:109 keeps NaN/Inf semantics)
           weight *= w;                  // rgen:110; the NEE sum is scaled by the post-BSDF weight
-          // next extension ray (rchit:462-463); the occlusion rays share its origin
-          // A ray that leaves a convex geometry to the front side of the triangle it starts on cannot meet that
-          // geometry again (k_batch_convex): the traversal stages skip the instance it starts on.  The test
-          // keeps a margin (sine of the elevation > 1e-3): a grazing ray takes the full walk, so that what
-          // rounding makes of a ray along its own surface stays what the oracle makes of it.
+          // next extension ray (rchit:462-463); the occlusion rays share its origin, whose spare word says which
+          // instance the two rays need not enter (leavesSurface):
           // instance | convex << 29 | extension ray skips it << 30 | occlusion ray skips it << 31
           uint32_t originBits = 0u;
           if (OWN) {
