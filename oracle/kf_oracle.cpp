@@ -28,6 +28,10 @@
 //       number from a hash of (ray.seed, instance, primitive) instead of advancing ray.seed in
 //       hardware traversal order, which is implementation-defined (the shim runs the real
 //       PathTrace.rahit; the two agree statistically, tests/test_cpu_ref_pin.py).
+//   D6  (the CUDA path only; mirrored here on request, kfo_set_skip_own_instance, to pin it) a bounce or
+//       occlusion ray that leaves a convex geometry to the front side of the triangle it starts on, by more
+//       than 1e-3 rad, does not enter the instance it starts on.  In exact arithmetic it cannot hit it;
+//       tests/test_cpu_oracle.py renders with and without and compares.
 //
 // Arithmetic contract (shared with the CUDA kernels so that hit buffers can be bit-exact):
 // IEEE-754 binary32, round-to-nearest, NO fused multiply-add in anything transcribed from the shaders
@@ -344,6 +348,7 @@ struct Geometry {
   bool opaque = true, hide = false, present = false;
   std::vector<Tri> tris;
   Bvh bvh;
+  bool convex = false;  // every vertex on or behind the plane of every triangle (the CUDA path's k_batch_convex)
 };
 
 struct Texture {
@@ -362,6 +367,11 @@ struct Counters {
 };
 
 struct Scene {
+  // Declared deviation D6 of the CUDA path, mirrored here on request (kfo_set_skip_own_instance) so that it can be
+  // pinned on the CPU: a bounce or occlusion ray that leaves a CONVEX geometry to the front side of the triangle it
+  // starts on, by more than a grazing margin, does not enter the instance it starts on.  Off by default: the
+  // oracle then walks every instance, as the reference does.
+  bool skipOwnInstance = false;
   std::vector<Geometry> geoms;
   std::vector<Material> mats;
   std::vector<Texture> texs;
@@ -446,6 +456,24 @@ static void buildAccel(Scene& s) {
       padBox(boxes[t]);
     }
     g.bvh.build(boxes, 4);
+    // convexity, the criterion of kf_blas_batch.cuh (k_batch_convex): tolerance 1e-5 of the extent
+    g.convex = false;
+    if (uint64_t(nt) * g.verts.size() <= (uint64_t(1) << 28) && !g.bvh.nodes.empty()) {
+      const Box& gb = g.bvh.nodes[0].box;
+      const float ext = std::fmax(gb.hi[0] - gb.lo[0], std::fmax(gb.hi[1] - gb.lo[1], gb.hi[2] - gb.lo[2]));
+      bool ok = true;
+      for (size_t t = 0; t < nt && ok; t++) {
+        const Tri& tr = g.tris[t];
+        const float nx = tr.e1.y * tr.e2.z - tr.e1.z * tr.e2.y, ny = tr.e1.z * tr.e2.x - tr.e1.x * tr.e2.z,
+                    nz = tr.e1.x * tr.e2.y - tr.e1.y * tr.e2.x;
+        const float tol = 1e-5f * ext * std::sqrt(nx * nx + ny * ny + nz * nz);
+        for (size_t v = 0; v < g.verts.size() && ok; v++) {
+          const float* q = g.verts[v].pos;
+          ok = nx * (q[0] - tr.v0.x) + ny * (q[1] - tr.v0.y) + nz * (q[2] - tr.v0.z) <= tol;
+        }
+      }
+      g.convex = ok;
+    }
   }
   s.instRt.resize(s.insts.size());
   std::vector<Box> ib(s.insts.size());
@@ -612,7 +640,7 @@ struct Tracer {
 
   // traceRayEXT equivalent.  tmax is exclusive (a hit needs tmin < t < tmax).
   bool trace(V3 o, V3 d, float tmin, float tmax, bool anyHit, uint32_t seed, bool terminateOnFirst,
-             Hit& out) const {
+             Hit& out, int32_t skipInst = -1) const {
     Hit best{};
     best.t = tmax;
     best.inst = -1;
@@ -622,6 +650,7 @@ struct Tracer {
     // while !found, so the initial best.t = tmax enforces the exclusive bound.
     if (brute || s.tlas.nodes.empty()) {
       for (uint32_t i = 0; i < s.instRt.size(); i++) {
+        if (int32_t(i) == skipInst) continue;
         traceInstance(i, o, d, tmin, anyHit, seed, best, found, terminateOnFirst);
         if (terminateOnFirst && found) break;
       }
@@ -635,6 +664,7 @@ struct Tracer {
         if (!slab(n.box, o, id, tmin, best.t)) continue;
         if (n.left < 0) {
           for (int k = n.first; k < n.first + n.count; k++) {
+            if (int32_t(s.tlas.order[k]) == skipInst) continue;
             traceInstance(s.tlas.order[k], o, d, tmin, anyHit, seed, best, found, terminateOnFirst);
             if (terminateOnFirst && found) break;
           }
@@ -737,6 +767,7 @@ struct RayPayLoad {  // base/Ray.glsl:1-14
   uint32_t seed, depth, type;
   V3 shadow_color;
   bool refractive;
+  int32_t skipInst = -1;  // D6 (Scene::skipOwnInstance): the instance the NEXT extension ray does not enter
 };
 
 struct Shader {
@@ -760,7 +791,16 @@ struct Shader {
   struct HitCtx {
     bool backFacing;
     V3 rayDirection;  // ray.direction at hit time (not yet overwritten)
+    // D6 (Scene::skipOwnInstance): instance of the hit and the geometric normal e1 x e2 of its triangle taken to
+    // world space like a shading normal; inst < 0 when the option is off or the geometry is not convex
+    int32_t inst = -1;
+    V3 Ng = {0.0f, 0.0f, 0.0f};
   };
+  // the CUDA path's leavesSurface(): to the front side of the triangle, by more than a grazing margin
+  static bool leavesSurface(V3 Ng, V3 d) {
+    const float sd = dot(Ng, d);
+    return sd > 0.0f && sd * sd > 1e-6f * dot(Ng, Ng) * dot(d, d);
+  }
 
   // PathTrace.rchit:103-171
   V3 calcDirectContribution(RayPayLoad& ray, const HitCtx& hc, V3 L, V3 V, V3 N, V3 lightEmission,
@@ -822,7 +862,8 @@ struct Shader {
       // TerminateOnFirstHit | Opaque | SkipClosestHitShader, miss index 1 (PathTraceShadow.rmiss)
       Hit h;
       shRays++;
-      isShadowed = tr.trace(worldPos, L, 0.001f, maxDist, /*anyHit=*/false, 0, true, h);
+      const int32_t skip = (hc.inst >= 0 && leavesSurface(hc.Ng, L)) ? hc.inst : -1;
+      isShadowed = tr.trace(worldPos, L, 0.001f, maxDist, /*anyHit=*/false, 0, true, h, skip);
     }
     return isShadowed ? v3(0.0f)
                       : calcDirectContribution(ray, hc, L, V, N, lightEmission, f, a2, diffuseColor,
@@ -1025,6 +1066,21 @@ struct Shader {
     }
 
     HitCtx hc{isInside, rayDirection};
+    ray.skipInst = -1;
+    if (s.skipOwnInstance && g.convex) {
+      const Tri& tr0 = g.tris[h.prim];
+      const V3 gn = {tr0.e1.y * tr0.e2.z - tr0.e1.z * tr0.e2.y, tr0.e1.z * tr0.e2.x - tr0.e1.x * tr0.e2.z,
+                     tr0.e1.x * tr0.e2.y - tr0.e1.y * tr0.e2.x};
+      V3 Ng;
+      Ng.x = (gn.x * ir.inv[0][0] + gn.y * ir.inv[1][0]) + gn.z * ir.inv[2][0];
+      Ng.y = (gn.x * ir.inv[0][1] + gn.y * ir.inv[1][1]) + gn.z * ir.inv[2][1];
+      Ng.z = (gn.x * ir.inv[0][2] + gn.y * ir.inv[1][2]) + gn.z * ir.inv[2][2];
+      if (Ng.x != 0.0f || Ng.y != 0.0f || Ng.z != 0.0f) {
+        hc.inst = h.inst;
+        hc.Ng = Ng;
+        if (leavesSurface(Ng, L)) ray.skipInst = h.inst;
+      }
+    }
     V3 sc = traceDirectionalLight(ray, hc, worldPos, N, f, a2, diffuseColor, specularColor, transmissionColor);
     sc = sc + tracePointLights(ray, hc, worldPos, N, f, a2, diffuseColor, specularColor, transmissionColor);
     sc = sc + traceActiveLights(ray, hc, worldPos, N, f, a2, diffuseColor, specularColor, transmissionColor);
@@ -1095,6 +1151,7 @@ static void raygenPixel(Shader& sh, const Camera& cam, uint32_t w, uint32_t h, u
     ray.refractive = false;
     ray.type = 0;
     ray.shadow_color = v3(0.0f);
+    ray.skipInst = -1;
 
     V3 weight = v3(1.0f);
     V3 color = v3(0.0f);
@@ -1105,7 +1162,7 @@ static void raygenPixel(Shader& sh, const Camera& cam, uint32_t w, uint32_t h, u
       Hit hit;
       sh.extRays++;
       V3 ro = ray.origin, rd = ray.direction;
-      bool found = sh.tr.trace(ro, rd, tMin, tMax, /*anyHit=*/true, ray.seed, false, hit);
+      bool found = sh.tr.trace(ro, rd, tMin, tMax, /*anyHit=*/true, ray.seed, false, hit, ray.skipInst);
       if (i == 0 && ray.depth == 0) {
         if (found) {
           hitInst = hit.inst;
@@ -1231,6 +1288,11 @@ int kfo_set_transforms(void* h, const float* transforms, uint32_t n) {
   if (n != s.insts.size()) return 1;
   for (uint32_t i = 0; i < n; i++) std::memcpy(s.insts[i].transform, transforms + 16 * i, 64);
   s.accelDirty = true;
+  return 0;
+}
+// D6 mirror (see Scene::skipOwnInstance); off by default.
+int kfo_set_skip_own_instance(void* h, int on) {
+  static_cast<Scene*>(h)->skipOwnInstance = on != 0;
   return 0;
 }
 int kfo_set_lights(void* h, const void* dl, const void* pl, const void* al) {

@@ -39,6 +39,7 @@ def load():
     lib.kfo_set_instances.argtypes = [vp, vp, u32]
     lib.kfo_set_transforms.argtypes = [vp, vp, u32]
     lib.kfo_set_lights.argtypes = [vp, vp, vp, vp]
+    lib.kfo_set_skip_own_instance.argtypes = [vp, i32]
     lib.kfo_render.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.kfo_resolve.argtypes = [vp, vp, vp, vp, C.c_uint64, u32, C.c_int32]
     lib.kfo_hardware_threads.restype = i32
@@ -141,6 +142,10 @@ class Oracle:
         p = np.ascontiguousarray(points) if points is not None else None
         a = np.ascontiguousarray(actives) if actives is not None else None
         self._ck(self.lib.kfo_set_lights(self.h, _p(d), _p(p), _p(a)), "set_lights")
+
+    def set_skip_own_instance(self, on):
+        """Mirror of the CUDA path's declared deviation D6 (kf_oracle.cpp header); off by default."""
+        self._ck(self.lib.kfo_set_skip_own_instance(self.h, int(on)), "set_skip_own_instance")
 
     def render(self, cameras, width, height, pc, sample_begin=0, sample_end=None, clock_base=0,
                brute=False, threads=0):
