@@ -123,3 +123,36 @@ def test_config_golden(built, case):
         assert np.array_equal(out[k], g[k]), k
     assert np.allclose(out["sum"], g["sum"], rtol=1e-5, atol=1e-6)
     assert (np.abs(out["bgra"].astype(int) - g["bgra"].astype(int)) > 1).mean() < 1e-3
+
+
+def test_header_structs_match_the_python_mirrors(tmp_path):
+    """include/kf_rt.h compiled as C: the sizes and field offsets of the structs that cross the ABI equal those of
+    the numpy mirrors in kuafu_b200/wire.py (the mirrors are what the tests and bench.py read counters and
+    statistics through)."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from kuafu_b200 import wire
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"KfrtCounters": wire.COUNTERS, "KfrtBvhStats": wire.BVH_STATS, "KfrtInstance": wire.INSTANCE,
+               "KfrtCamera": wire.CAMERA, "KfrtPushConstants": wire.PUSH_CONSTANTS, "KfrtVertex": wire.VERTEX,
+               "KfrtMaterial": wire.MATERIAL}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "kf_rt.h"', 'int main(void) {']
+    by_field = ("KfrtCounters", "KfrtBvhStats")  # mirrored field by field (the others pad under other names)
+    for name, dt in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field in (dt.names if name in by_field else ()):
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([cc, "-std=c99", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, dt in structs.items():
+        assert int(got[name]) == dt.itemsize, (name, got[name], dt.itemsize)
+        for field in (dt.names if name in by_field else ()):
+            assert int(got[f"{name}.{field}"]) == dt.fields[field][1], (name, field)
