@@ -372,6 +372,12 @@ struct Scene {
   // starts on, by more than a grazing margin, does not enter the instance it starts on.  Off by default: the
   // oracle then walks every instance, as the reference does.
   bool skipOwnInstance = false;
+  // The CUDA path's light-sample culling (kf_wavefront.cuh, nextRelevantLight), mirrored on request
+  // (kfo_set_cull_light_samples) so that "cannot matter" can be checked where no kernel is involved: a light
+  // sample whose contribution is exactly zero and draws no random number, or -- in a scene with a single light
+  // slot -- any finite sample of a path whose BSDF weight is exactly zero, is answered without a ray.
+  bool cullLightSamples = false;
+  uint64_t lastShadowSkipped = 0;  // light samples the last kfo_render answered without a ray (kfo_last_shadow_skipped)
   std::vector<Geometry> geoms;
   std::vector<Material> mats;
   std::vector<Texture> texs;
@@ -774,8 +780,17 @@ struct Shader {
   const Scene& s;
   const PushConstants& pc;
   Tracer tr;
-  uint64_t extRays = 0, shRays = 0, extHits = 0;
+  uint64_t extRays = 0, shRays = 0, extHits = 0, shSkipped = 0;
+  bool deadPath = false;  // cullLightSamples: the BSDF sample of the hit being shaded has weight exactly zero
   Shader(const Scene& sc, const PushConstants& p, bool brute) : s(sc), pc(p), tr(sc, brute) {}
+  // the number of light slots that are switched on, by the CUDA path's conditions (kfrtSetLights)
+  uint32_t lightSlots() const {
+    uint32_t n = 0;
+    if (s.dl.rgbs[0] * s.dl.rgbs[3] != 0 || s.dl.rgbs[1] * s.dl.rgbs[3] != 0 || s.dl.rgbs[2] * s.dl.rgbs[3] != 0) n++;
+    for (int i = 0; i < 32; i++) n += s.pl.rgbs[i][3] > 0 ? 1u : 0u;
+    for (int i = 0; i < 8; i++) n += s.al.front[i][3] > 0 ? 1u : 0u;
+    return n;
+  }
 
   // PathTrace.rmiss:12-31
   void miss(RayPayLoad& ray) {
@@ -860,6 +875,17 @@ struct Shader {
     float NdotL = dot(N, L);
     if (NdotL > 0.0f) {
       // TerminateOnFirstHit | Opaque | SkipClosestHitShader, miss index 1 (PathTraceShadow.rmiss)
+      if (s.cullLightSamples) {
+        RayPayLoad probe = ray;
+        const V3 c = calcDirectContribution(probe, hc, L, V, N, lightEmission, f, a2, diffuseColor, specularColor,
+                                            transmissionColor);
+        const bool zeroNoDraw = allEq(c, v3(0.0f)) && probe.seed == ray.seed;
+        const bool finite = std::isfinite(c.x) && std::isfinite(c.y) && std::isfinite(c.z);
+        if (zeroNoDraw || (deadPath && finite && lightSlots() <= 1)) {
+          shSkipped++;
+          return v3(0.0f);
+        }
+      }
       Hit h;
       shRays++;
       const int32_t skip = (hc.inst >= 0 && leavesSurface(hc.Ng, L)) ? hc.inst : -1;
@@ -1066,6 +1092,7 @@ struct Shader {
     }
 
     HitCtx hc{isInside, rayDirection};
+    deadPath = allEq(weight, v3(0.0f));
     ray.skipInst = -1;
     if (s.skipOwnInstance && g.convex) {
       const Tri& tr0 = g.tris[h.prim];
@@ -1295,6 +1322,12 @@ int kfo_set_skip_own_instance(void* h, int on) {
   static_cast<Scene*>(h)->skipOwnInstance = on != 0;
   return 0;
 }
+// Mirror of the CUDA path's light-sample culling (see Scene::cullLightSamples); off by default.
+int kfo_set_cull_light_samples(void* h, int on) {
+  static_cast<Scene*>(h)->cullLightSamples = on != 0;
+  return 0;
+}
+unsigned long long kfo_last_shadow_skipped(void* h) { return static_cast<Scene*>(h)->lastShadowSkipped; }
 int kfo_set_lights(void* h, const void* dl, const void* pl, const void* al) {
   Scene& s = *static_cast<Scene*>(h);
   if (dl) std::memcpy(&s.dl, dl, sizeof(DirLight)); else std::memset(&s.dl, 0, sizeof(DirLight));
@@ -1323,7 +1356,7 @@ int kfo_render(void* h, const void* cams, uint32_t nCams, uint32_t w, uint32_t h
   int nt = threads > 0 ? threads : int(std::thread::hardware_concurrency());
   if (nt < 1) nt = 1;
   std::atomic<uint64_t> nextRow{0};
-  std::atomic<uint64_t> cExt{0}, cSh{0}, cHit{0};
+  std::atomic<uint64_t> cExt{0}, cSh{0}, cHit{0}, cSkip{0};
   uint64_t totalRows = uint64_t(nCams) * ht;
   auto worker = [&]() {
     Shader sh(s, pc, mode == 1);
@@ -1341,11 +1374,13 @@ int kfo_render(void* h, const void* cams, uint32_t nCams, uint32_t w, uint32_t h
     cExt += sh.extRays;
     cSh += sh.shRays;
     cHit += sh.extHits;
+    cSkip += sh.shSkipped;
   };
   std::vector<std::thread> pool;
   for (int t = 1; t < nt; t++) pool.emplace_back(worker);
   worker();
   for (auto& t : pool) t.join();
+  s.lastShadowSkipped = cSkip;
   if (counters) {
     counters[0] = uint64_t(nCams) * w * ht * (s1 - s0);
     counters[1] = cExt;

@@ -40,6 +40,9 @@ def load():
     lib.kfo_set_transforms.argtypes = [vp, vp, u32]
     lib.kfo_set_lights.argtypes = [vp, vp, vp, vp]
     lib.kfo_set_skip_own_instance.argtypes = [vp, i32]
+    lib.kfo_set_cull_light_samples.argtypes = [vp, i32]
+    lib.kfo_last_shadow_skipped.argtypes = [vp]
+    lib.kfo_last_shadow_skipped.restype = C.c_uint64
     lib.kfo_render.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.kfo_resolve.argtypes = [vp, vp, vp, vp, C.c_uint64, u32, C.c_int32]
     lib.kfo_hardware_threads.restype = i32
@@ -146,6 +149,13 @@ class Oracle:
     def set_skip_own_instance(self, on):
         """Mirror of the CUDA path's declared deviation D6 (kf_oracle.cpp header); off by default."""
         self._ck(self.lib.kfo_set_skip_own_instance(self.h, int(on)), "set_skip_own_instance")
+
+    def set_cull_light_samples(self, on):
+        """Mirror of the CUDA path's light-sample culling (kf_oracle.cpp, Scene::cullLightSamples); off by default."""
+        self._ck(self.lib.kfo_set_cull_light_samples(self.h, int(on)), "set_cull_light_samples")
+
+    def last_shadow_skipped(self):
+        return int(self.lib.kfo_last_shadow_skipped(self.h))
 
     def render(self, cameras, width, height, pc, sample_begin=0, sample_end=None, clock_base=0,
                brute=False, threads=0):
