@@ -104,6 +104,28 @@ def test_budget_keeps_large_scenes_two_level(rt):
 
 
 @pytest.mark.parametrize("lights", ["dir", "dir point active"])
+def test_culled_light_samples_are_the_ones_the_oracle_would_cull(rt, orc_mod, lights):
+    """The kernel's light-sample culling against the oracle's mirror of the rule (kfo_set_cull_light_samples, which
+    tests/test_cpu_oracle.py shows to change no bit of the frame): the same light samples are traced and the
+    same are answered without a ray (measured: 46 777 / 1 156 and 192 454 / 5 496 on both sides; the bound
+    leaves room for a path whose length flips on an ulp)."""
+    sc = pyscene.small_scene(seed=11, w=160, h=120, spp=4, depth=8, lights=lights, textures=True, glass=True)
+    ctx = rt.Context(0)
+    sc.upload(ctx)
+    ctx.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, None, 3)
+    c = ctx.counters()
+    orc = orc_mod.Oracle()
+    sc.upload(orc)
+    orc.set_cull_light_samples(True)
+    ref = orc.render(np.array(sc.cams, wire.CAMERA), sc.w, sc.h, sc.pc, 0, None, 3)
+    traced, skipped = ref["counters"]["shadowRays"], orc.last_shadow_skipped()
+    assert skipped > 0
+    assert abs(int(c["shadowRays"]) - traced) <= 0.005 * traced, (int(c["shadowRays"]), traced)
+    assert abs(int(c["shadowRaysSkipped"]) - skipped) <= max(8, 0.02 * skipped), (int(c["shadowRaysSkipped"]), skipped)
+    ctx.close()
+
+
+@pytest.mark.parametrize("lights", ["dir", "dir point active"])
 def test_culled_light_samples_change_nothing(rt, lights):
     """kfrtSetLightSampleCulling / kfrtSetOwnInstanceSkip: with both off every light sample the reference traces
     is traced and every ray walks every instance on its way; with them on (the default) the first-hit buffers
